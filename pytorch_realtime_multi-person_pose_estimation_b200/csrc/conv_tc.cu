@@ -1,0 +1,342 @@
+// tcgen05 "halo-patch" implicit-GEMM convolution for sm_100a (B200).
+//
+// Computes, for every conv of the rtpose VGG19 net with Cin >= 64
+// (/root/reference/lib/network/rtpose_vgg.py:69-127), out = act(conv_kxk(in) + bias) with optional fused
+// MaxPool2d(2,2) and "concat by construction" (the epilogue writes straight into a channel slice of the
+// next layer's NHWC buffer, replacing torch.cat at rtpose_vgg.py:165,171,177,183,189).
+//
+// Mapping to the hardware (see DESIGN.md "conv_tc"):
+//   * A CTA owns a 16x16 block of output pixels = two UMMA M=128 sub-tiles of 8 (w) x 16 (h) pixels.
+//   * For each 64-channel block of the input, ONE TMA 4-D tile load brings the (16+k-1) x 24 pixel halo patch
+//     (NHWC bf16, 128 B per pixel, SWIZZLE_128B, out-of-image pixels zero-filled by TMA = conv padding) into
+//     shared memory.  Every one of the k*k filter taps then reads its shifted 8x16 window of that SAME patch
+//     directly through the UMMA shared-memory descriptor (start address = patch + (dy*24+dx)*128 B,
+//     8-row groups 24*128 B apart), so the activation tile is fetched from L2 once instead of k*k times.
+//   * Per tap, a TMA 3-D load brings the [n_tile x 64] weight slice (K-major, SWIZZLE_128B) into a 5-deep ring.
+//   * One elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) into TMEM; two accumulator sets
+//     (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//   * Four epilogue warps read TMEM (tcgen05.ld 32x32b), add bias, ReLU, optionally 2x2 max-pool through warp
+//     shuffles, convert to bf16 and store NHWC; the stage heads additionally emit the fp32 NCHW outputs.
+//   * Persistent grid (one CTA per SM), static round-robin tile schedule.
+#include <cstdio>
+
+#include "conv_tc.cuh"
+#include "ptx.cuh"
+
+namespace b2p {
+
+namespace {
+
+struct TileCoord {
+    int n, y0, x0, g, nt;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int groups, int tiles_x, int tiles_y) {
+    TileCoord c;
+    c.nt = t % n_tiles;
+    t /= n_tiles;
+    c.g = t % groups;
+    t /= groups;
+    c.x0 = (t % tiles_x) * kTileW;
+    t /= tiles_x;
+    c.y0 = (t % tiles_y) * kTileH;
+    c.n = t / tiles_y;
+    return c;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024 B alignment.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* patch_smem = smem;
+    uint8_t* b_smem = smem + kNumPatchStages * kPatchBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * kBStageBytes);
+    uint64_t* patch_full = bars;                          // [2]
+    uint64_t* patch_empty = bars + kNumPatchStages;       // [2]
+    uint64_t* b_full = bars + 2 * kNumPatchStages;        // [5]
+    uint64_t* b_empty = b_full + kNumBStages;             // [5]
+    uint64_t* acc_full = b_empty + kNumBStages;           // [2]
+    uint64_t* acc_empty = acc_full + 2;                   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tiles_x = (a.W + kTileW - 1) / kTileW;
+    const int tiles_y = (a.H + kTileH - 1) / kTileH;
+    const int total_tiles = a.n_img * tiles_y * tiles_x * a.groups * a.n_tiles;
+    const int taps = a.ksize * a.ksize;
+    const int pad = a.ksize >> 1;
+    const uint32_t patch_tx = kPatchPitch * (kTileH + a.ksize - 1) * 128;
+    const uint32_t b_tx = a.n_tile * 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&a.tm_in);
+        tma_prefetch_desc(&a.tm_w);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < kNumPatchStages; ++i) {
+                mbar_init(&patch_full[i], 1);
+                mbar_init(&patch_empty[i], 1);
+            }
+            for (int i = 0; i < kNumBStages; ++i) {
+                mbar_init(&b_full[i], 1);
+                mbar_init(&b_empty[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&acc_full[i], 1);
+                mbar_init(&acc_empty[i], 4);   // one arrive per epilogue warp
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =========================== TMA producer: activation halo patches ===========================
+        if (lane == 0) {
+            uint32_t pi = 0, pph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
+                const int ch0 = a.in_ch_base + tc.g * a.in_ch_group_stride;
+                for (int cb = 0; cb < a.cin_blocks; ++cb) {
+                    mbar_wait(&patch_empty[pi], pph ^ 1, 1);
+                    mbar_expect_tx(&patch_full[pi], patch_tx);
+                    tma_load_4d(patch_smem + pi * kPatchBytes, &a.tm_in, &patch_full[pi], ch0 + cb * 64, tc.x0 - pad,
+                                tc.y0 - pad, tc.n);
+                    if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // =========================== TMA producer: weight slices ===========================
+        if (lane == 0) {
+            uint32_t bi = 0, bph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
+                const int wrow = (tc.g * a.n_tiles + tc.nt) * a.n_tile;
+                for (int cb = 0; cb < a.cin_blocks; ++cb) {
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&b_empty[bi], bph ^ 1, 2);
+                        mbar_expect_tx(&b_full[bi], b_tx);
+                        tma_load_3d(b_smem + bi * kBStageBytes, &a.tm_w, &b_full[bi], cb * 64, wrow, tap);
+                        if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16_m128(a.n_tile);
+            const uint32_t patch_addr0 = smem_u32(patch_smem);
+            const uint32_t b_addr0 = smem_u32(b_smem);
+            uint32_t pi = 0, pph = 0, bi = 0, bph = 0, ai = 0, aph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(&acc_empty[ai], aph ^ 1, 3);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ai * 256;
+                for (int cb = 0; cb < a.cin_blocks; ++cb) {
+                    mbar_wait(&patch_full[pi], pph, 4);
+                    const uint32_t patch_addr = patch_addr0 + pi * kPatchBytes;
+                    int dy = 0, dx = 0;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(&b_full[bi], bph, 5);
+                        tc_fence_after();
+                        const uint32_t b_addr = b_addr0 + bi * kBStageBytes;
+                        const uint32_t boff = a.use_base_offset ? (dx & 7) : 0;
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const uint32_t a_addr = patch_addr + (dy * kPatchPitch + dx + sub * 8) * 128;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, kPatchPitch * 128, boff);
+                                const uint64_t bdesc = make_sdesc_sw128(b_addr + k * 32, 1024, 0);
+                                umma_bf16(d_tmem + sub * 128, adesc, bdesc, idesc, (cb | tap | k) != 0);
+                            }
+                        }
+                        umma_commit(&b_empty[bi]);
+                        if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
+                        if (++dx == a.ksize) { dx = 0; ++dy; }
+                    }
+                    umma_commit(&patch_empty[pi]);
+                    if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; }
+                }
+                umma_commit(&acc_full[ai]);
+                if (++ai == 2) { ai = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 2..5) ===========================
+        // (warp & 3) = 2,3,0,1: each warp may only touch its own quarter of the 128 TMEM lanes.
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int h_in = q * 4 + (lane >> 3);
+        const int w_in = lane & 7;
+        const int Ho = a.pool ? a.H >> 1 : a.H;
+        const int Wo = a.pool ? a.W >> 1 : a.W;
+        uint32_t ai = 0, aph = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
+            mbar_wait(&acc_full[ai], aph, 6);
+            tc_fence_after();
+            const int ch_tile = tc.nt * a.n_tile;                    // first channel of this n-tile within the group
+            const float* bias = a.bias + (tc.g * a.n_tiles + tc.nt) * a.n_tile;
+            const int store_ch = a.store_ch[tc.g];
+            float* of32 = a.out_f32[tc.g];
+            const int f32_ch = a.f32_ch[tc.g];
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                const int y = tc.y0 + h_in;
+                const int x = tc.x0 + sub * 8 + w_in;
+                const bool valid = (y < a.H) && (x < a.W);
+                // pooled: lanes with even (h, w) own the 2x2 window
+                const bool writer = a.pool ? (valid && !(lane & 1) && !(lane & 8)) : valid;
+                const int yo = a.pool ? y >> 1 : y;
+                const int xo = a.pool ? x >> 1 : x;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ai * 256 + sub * 128;
+#pragma unroll 1
+                for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+                        if (a.relu) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (a.pool) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+                        }
+                    }
+                    if (writer) {
+                        if (a.out != nullptr) {
+                            __nv_bfloat16* dst = a.out + (static_cast<size_t>(tc.n * Ho + yo) * Wo + xo) * a.out_cstride +
+                                                 a.out_ch_off[tc.g] + ch_tile + c0;
+                            if (c0 < store_ch) {
+                                uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                     pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                                *reinterpret_cast<uint4*>(dst) = u;
+                            }
+                            if (c0 + 8 < store_ch) {
+                                uint4 u = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
+                                                     pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                                *reinterpret_cast<uint4*>(dst + 8) = u;
+                            }
+                        }
+                        if (of32 != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int c = ch_tile + c0 + j;
+                                if (c < f32_ch)
+                                    of32[(static_cast<size_t>(tc.n * f32_ch + c) * Ho + yo) * Wo + xo] = v[j];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ai]);
+            if (++ai == 2) { ai = 0; aph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cstride, const __nv_bfloat16* w) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (enc == nullptr) return cudaErrorNotSupported;
+    if (a.ksize != 1 && a.ksize != 3 && a.ksize != 7) return cudaErrorInvalidValue;
+    if (a.n_tile % 16 != 0 || a.n_tile < 16 || a.n_tile > 128) return cudaErrorInvalidValue;
+    if (a.groups < 1 || a.groups > 2 || in_cstride % 8 != 0) return cudaErrorInvalidValue;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)in_cstride, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n_img};
+        cuuint64_t strides[3] = {(cuuint64_t)in_cstride * 2, (cuuint64_t)a.W * in_cstride * 2,
+                                 (cuuint64_t)a.H * a.W * in_cstride * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)kPatchPitch, (cuuint32_t)(kTileH + a.ksize - 1), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&a.tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "[b200pose] cuTensorMapEncodeTiled(in) failed: %d\n", (int)r);
+            return cudaErrorInvalidValue;
+        }
+    }
+    {
+        const int cin_pad = a.cin_blocks * 64;
+        const int rows = a.groups * a.n_tiles * a.n_tile;
+        const int taps = a.ksize * a.ksize;
+        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)rows, (cuuint64_t)taps};
+        cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)rows * cin_pad * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)a.n_tile, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&a.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(w), dims, strides,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "[b200pose] cuTensorMapEncodeTiled(w) failed: %d\n", (int)r);
+            return cudaErrorInvalidValue;
+        }
+    }
+    return cudaSuccess;
+}
+
+cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e =
+            cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (a.pool && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
+    const int tiles_x = (a.W + kTileW - 1) / kTileW;
+    const int tiles_y = (a.H + kTileH - 1) / kTileH;
+    const int total = a.n_img * tiles_y * tiles_x * a.groups * a.n_tiles;
+    const int grid = total < num_sms ? total : num_sms;
+    conv_tc_kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace b2p

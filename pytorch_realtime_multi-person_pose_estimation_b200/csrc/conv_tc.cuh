@@ -1,0 +1,54 @@
+// Host-side interface of the tcgen05 "halo-patch" implicit-GEMM convolution (conv_tc.cu).
+// Replaces the nn.Conv2d(+ReLU)(+MaxPool2d)(+torch.cat) sequences of
+// /root/reference/lib/network/rtpose_vgg.py:23-29,165 for every conv with Cin >= 64.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace b2p {
+
+constexpr int kTileW = 16;        // CTA tile: 16 x 16 output pixels = two 8-wide x 16-high UMMA M=128 sub-tiles
+constexpr int kTileH = 16;
+constexpr int kPatchPitch = 24;   // patch row pitch in pixels (16 + 6 halo, rounded up to a multiple of 8)
+constexpr int kMaxKs = 7;
+constexpr int kPatchBytes = kPatchPitch * (kTileH + kMaxKs - 1) * 128;  // 67,584 B per 64-channel block
+constexpr int kBStageBytes = 128 * 128;                                 // up to N=128 rows of 64 bf16
+constexpr int kNumBStages = 5;
+constexpr int kNumPatchStages = 2;
+constexpr int kConvTcThreads = 224;   // warps: 0 patch TMA, 1 MMA, 2-5 epilogue, 6 weight TMA
+constexpr int kConvTcSmemBytes = kNumPatchStages * kPatchBytes + kNumBStages * kBStageBytes + 1024 /*align*/ + 256;
+
+struct ConvTcArgs {
+    // ---- geometry (stride 1, "same" padding, square kernel)
+    int n_img, H, W;
+    int ksize;                // 1, 3 or 7
+    int cin_blocks;           // 64-channel blocks per group
+    int in_ch_base;           // first input channel (in the NHWC buffer) of group 0
+    int in_ch_group_stride;   // channel offset between groups in the input buffer (0 = groups share input)
+    int groups;               // 1 or 2
+    int n_tile;               // UMMA N: multiple of 16, <= 128
+    int n_tiles;              // N tiles per group
+    // ---- epilogue
+    const float* bias;        // [groups * n_tiles * n_tile]
+    int relu;
+    int pool;                 // fuse MaxPool2d(2,2): output is (H/2, W/2)
+    __nv_bfloat16* out;       // NHWC bf16 (may be null)
+    int out_cstride;          // channels per pixel of the output buffer
+    int out_ch_off[2];        // first output channel per group
+    int store_ch[2];          // channels (multiple of 8) stored per group *per n-tile*
+    float* out_f32[2];        // optional NCHW fp32 copy per group (heads), may be null
+    int f32_ch[2];            // valid channels of the fp32 copy
+    int use_base_offset;      // descriptor swizzle-phase field
+    // ---- tensor maps
+    CUtensorMap tm_in;        // 4D (C, W, H, N) bf16, box (64, 24, 16+ks-1, 1), SWIZZLE_128B
+    CUtensorMap tm_w;         // 3D (cin_pad, groups*n_tiles*n_tile, taps) bf16, box (64, n_tile, 1), SWIZZLE_128B
+};
+
+// Builds the two tensor maps. `in`: NHWC buffer with `in_cstride` channels per pixel. `w`: packed weights
+// [taps][groups*n_tiles*n_tile][cin_blocks*64].
+cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cstride, const __nv_bfloat16* w);
+cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream);
+
+}  // namespace b2p
