@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: frames/sec end-to-end (rtpose VGG19 net + fused pafprocess) at 368x368.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference algorithm on the host CPU cores)
+
+One "step" = one pass of the hot path over one batch of 32 synthetic frames per GPU (BASELINE.json configs[2] /
+configs[3]: batch 32 per B200, bf16, fused post-processing).  Weights: seeded He-normal, inputs:
+seeded uniform [-0.5, 0.5).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec end-to-end (net+pafprocess) @368x368"
+UNIT = "frames/s"
+BATCH, H, W = 32, 368, 368
+FLOPS_PER_FRAME = 271868013568.0        # convolution FLOPs per 368x368 frame
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.split(",") for l in open(self.f.name).read().strip().splitlines() if l.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return None
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][2]),
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows), "reasons": sorted(reasons)}
+
+
+def synthetic_weights():
+    import _b200_alias
+    return importlib.import_module(_b200_alias.PKG + ".synthetic").he_state_arrays(1234)
+
+
+def run_ours(args):
+    import torch
+    import _b200_alias
+    _b200_alias.load_package()
+    engine = importlib.import_module(_b200_alias.PKG + ".engine")
+    nat = importlib.import_module(_b200_alias.PKG + "._native")
+    dist_mod = importlib.import_module(_b200_alias.PKG + ".distributed")
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        arrays = dist_mod.broadcast_state_arrays(synthetic_weights() if rank == 0 else None, device=dev)
+    else:
+        arrays = synthetic_weights()
+    eng = engine.PoseEngine(arrays, local, mode="bf16", batch_cap=BATCH, peak_cap=1024, human_cap=1024)
+
+    # 4 rotating device inputs (4 x 52 MB > 126 MB L2) + 2 pinned host inputs; per-rank seed
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [(torch.rand((BATCH, 3, H, W), generator=g) - 0.5).pin_memory() for _ in range(2)]
+    devin = [host[i % 2].to(dev) + 0.001 * i for i in range(4)]
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        eng.infer_async(devin[i % 4].data_ptr(), True, BATCH, H, W, 0.1, sptr)
+
+    d2h_bytes = []
+
+    def step_e2e(i):
+        eng.infer_async(host[i % 2].data_ptr(), False, BATCH, H, W, 0.1, sptr)
+        eng.post.sync()
+        nh = 0
+        for k in range(BATCH):
+            nh += len(eng.post.humans(k))
+        d2h_bytes.append(4 * BATCH * (1 + 1 + 18) + nh * 73 * 4)
+
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    st0 = eng.post.status(0)
+
+    # ---- device-resident timing (value)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1)
+    launches = nat.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    barrier()
+
+    # ---- end-to-end timing through the public API with host buffers (e2e)
+    for i in range(2):
+        step_e2e(i)
+    d2h_bytes.clear()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    barrier()
+
+    if world > 1:
+        ms_dev = dist_mod.max_over_ranks(ms_dev, dev)
+        ms_e2e = dist_mod.max_over_ranks(ms_e2e, dev)
+
+    # ---- roofline of the dominant kernel (conv_tc_kernel), measured live: per-launch CUDA events
+    roof = None
+    if rank == 0:
+        import ctypes
+        step_device(0)
+        torch.cuda.synchronize()
+        cap = 64
+        ms = (ctypes.c_float * cap)()
+        fl = (ctypes.c_double * cap)()
+        tot_ms, tot_fl, nl = 0.0, 0.0, 0
+        for _ in range(3):
+            nl = nat.lib().b200pose_net_profile(eng.net._h, ms, fl, cap, ctypes.c_void_p(sptr))
+            if nl <= 0:
+                break
+            tot_ms += sum(ms[i] for i in range(1, nl))
+            tot_fl += sum(fl[i] for i in range(1, nl))
+        pk_tf, pk_bw, pk_src = peaks()
+        if nl > 0 and tot_ms > 0:
+            ach = tot_fl / (tot_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "conv_tc_kernel (51 launches/step, all tcgen05 convs)",
+                    "achieved": round(ach, 1), "peak": pk_tf, "unit": "TFLOP/s", "frac": round(ach / pk_tf, 4),
+                    "traffic": None, "peak_source": pk_src,
+                    "share_of_step": round(tot_ms / 3 / (ms_dev / args.steps), 3)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames = BATCH * world * args.steps
+    value = frames / (ms_dev * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    cpu = cpu_baseline_sample(frames=2) if world == 1 and not args.no_cpu_baseline else None
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "batch=32 per GPU, 368x368, rtpose VGG19 bf16 (tcgen05) + fused NMS/PAF-match/assembly "
+                               "(BASELINE.json configs[2]; configs[3] when n_gpus=8)",
+                   "global_batch": BATCH * world, "weights": "He-normal seed 1234 (random init)",
+                   "l2": "inputs rotate over 4 device buffers (208 MB > 126 MB L2); ~1.4 GB of activations per step",
+                   "parallelism": "dp%d (frames sharded, one NCCL weight broadcast)" % world,
+                   "post_status_bits": int(st0)},
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
+                "d2h_bytes_per_step": int(np.mean(d2h_bytes)) if d2h_bytes else 0,
+                "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "net_tflops_device": round(FLOPS_PER_FRAME * frames / (ms_dev * 1e-3) / 1e12 / world, 1),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_frame_fn():
+    """The reference algorithm on the host: oracle port of rtpose_model.forward (torch CPU fp32) + NMS + the
+    C pafprocess (oracle/_ref when it was built from the reference sources, else the plain-C port)."""
+    import torch
+    from oracle import glue_port, net_port, pafprocess_oracle
+    torch.set_num_threads(os.cpu_count())
+    sd = net_port.he_state_dict(1234)
+    if pafprocess_oracle.have_ref():
+        paf_lib, kind = pafprocess_oracle.load_ref(), "reference pafprocess.cpp + oracle port of the torch/numpy glue"
+    else:
+        paf_lib, kind = pafprocess_oracle.load_port(), "port"
+    g = torch.Generator().manual_seed(1234)
+
+    def one_frame():
+        x = torch.rand((1, 3, H, W), generator=g) - 0.5
+        with torch.no_grad():
+            (paf, heat), _ = net_port.forward(sd, x)          # get_outputs minus image I/O (coco_eval.py:105-112)
+        heat = heat.numpy().transpose(0, 2, 3, 1)[0]
+        paf = paf.numpy().transpose(0, 2, 3, 1)[0]
+        return glue_port.paf_to_pose(heat, paf, paf_lib)      # paf_to_pose_cpp (paf_to_pose.py:372-406)
+    return one_frame, kind
+
+
+def cpu_baseline_sample(frames=2):
+    one_frame, kind = cpu_frame_fn()
+    one_frame()
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        one_frame()
+    dt = time.perf_counter() - t0
+    return {"value": round(frames / dt, 4), "unit": UNIT, "cores": os.cpu_count(),
+            "kind": "port" if kind == "port" else "reference",
+            "sample": "%d frames of 368x368, batch 1, serial run_eval-style loop (%s), after 1 warm-up frame" % (frames, kind)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    one_frame, kind = cpu_frame_fn()
+    per_step = 1
+    for _ in range(min(args.warmup, 1)):
+        one_frame()
+    t0 = time.perf_counter()
+    for _ in range(args.steps * per_step):
+        one_frame()
+    dt = time.perf_counter() - t0
+    v = args.steps * per_step / dt
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batch=32 per GPU, 368x368, rtpose VGG19 + pafprocess; each step = a bounded sample "
+                                   "of %d frame(s) run serially at batch 1 on the host CPU" % per_step},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(),
+                             "kind": "port" if kind == "port" else "reference",
+                             "sample": "%d frame(s) per step, %d steps (%s)" % (per_step, args.steps, kind)},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

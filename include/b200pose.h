@@ -1,0 +1,110 @@
+/* b200pose - C ABI of the B200-native OpenPose (rtpose VGG19) inference path.
+ *
+ * Plain pointers and sizes only; no torch / numpy types.  Every entry point returns 0 on success and a
+ * non-zero code on failure (b200pose_last_error() gives the text) unless stated otherwise.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to /root/reference).
+ * The reference-side bindings (ctypes) are shown in INTEGRATION.md.
+ */
+#ifndef B200POSE_H
+#define B200POSE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 0. Library
+ * ---------------------------------------------------------------------------------------------------------- */
+const char* b200pose_last_error(void);
+int b200pose_version(void);
+/* Number of CUDA kernels launched by this library since load (the bench's gpu_launches evidence). */
+long b200pose_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 1. Network: replaces rtpose_model.forward                       lib/network/rtpose_vgg.py:158-198
+ *    (get_model / make_vgg19_block / make_stages                  lib/network/rtpose_vgg.py:13-56, 60-225)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b200pose_net b200pose_net;
+
+#define B200POSE_NUM_TENSORS 184   /* state_dict entries, reference order (model0, model{1..6}_1, model{1..6}_2) */
+#define B200POSE_MODE_BF16 0       /* tcgen05 tensor cores, bf16 operands, fp32 accumulate                       */
+#define B200POSE_MODE_FP32 1       /* fp32-parity mode: fp32 FMA everywhere (1e-3 bar of BASELINE.json)          */
+
+int b200pose_net_create(b200pose_net** out, int cuda_device);
+void b200pose_net_destroy(b200pose_net* net);
+/* Shape of state_dict tensor `index` (weights: 4 dims OIHW, biases: 1 dim); returns number of dims. */
+int b200pose_net_tensor_shape(int index, long dims[4]);
+/* Copy one fp32 tensor (host memory, OIHW / [O]) into the net.  Replaces load_state_dict(), demo/picture_demo.py:46. */
+int b200pose_net_set_tensor(b200pose_net* net, int index, const float* host_data, long count);
+/* Pack weights for the device (bf16 K-major slices, padded heads, concat-permuted 7x7 inputs). */
+int b200pose_net_finalize(b200pose_net* net);
+/* forward: input fp32 NCHW [n,3,H,W] (H, W multiples of 8); outputs[12] fp32 NCHW in saved_for_loss order
+ * [paf1, heat1, ..., paf6, heat6] (paf [n,38,H/8,W/8], heat [n,19,H/8,W/8]); entries may be NULL to skip the
+ * copy-out.  *_on_device: 0 = host pointers (copies are issued on `cuda_stream` and synchronised before return),
+ * 1 = device pointers (asynchronous on `cuda_stream`).  cuda_stream: a cudaStream_t cast to void* (NULL = default). */
+int b200pose_net_forward(b200pose_net* net, const float* input, int input_on_device, int n, int H, int W, int mode,
+                         float* const* outputs, int outputs_on_device, void* cuda_stream);
+/* Measurement hook: re-runs the launch list of the last bf16 forward (conv1_1 + 51 tensor-core launches) with a CUDA
+ * event pair around every launch; fills per-launch milliseconds and ALGORITHMIC FLOPs (2 x MACs of the unpadded
+ * convolution).  Returns the number of launches, < 0 on error. */
+int b200pose_net_profile(b200pose_net* net, float* ms, double* flops, int cap, void* cuda_stream);
+/* Device pointers of the last forward's stage-6 maps (NCHW fp32), valid until the next forward. */
+int b200pose_net_last_maps(b200pose_net* net, const float** paf, const float** heat, int* n, int* h, int* w);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 2. Post-processing: replaces NMS + paf_to_pose_cpp + pafprocess  lib/utils/paf_to_pose.py:67-145, 372-406
+ *                                                                  lib/pafprocess/pafprocess.cpp:22-218
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b200pose_post b200pose_post;
+
+#define B200POSE_HUMAN_FLOATS 73   /* score, then 18 x (x, y, peak score, peak id or -1); x, y in input pixels */
+/* status bits */
+#define B200POSE_ST_PEAK_OVERFLOW 1
+#define B200POSE_ST_CAND_OVERFLOW 2
+#define B200POSE_ST_ROW_OVERFLOW 4
+#define B200POSE_ST_HUMAN_OVERFLOW 8
+
+int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, int peak_cap_per_part, int human_cap);
+void b200pose_post_destroy(b200pose_post* post);
+/* heat [n,19,h,w], paf [n,38,h,w] (layout 0 = NCHW) or heat [n,h,w,19], paf [n,h,w,38] (layout 1 = NHWC, what
+ * get_outputs returns per image, evaluate/coco_eval.py:111-112); fp32, low resolution (stride 8).
+ * thresh = cfg.TEST.THRESH_HEATMAP.  Results stay on the device until fetched. */
+int b200pose_post_run(b200pose_post* post, const float* heat, const float* paf, int on_device, int layout, int n, int h,
+                      int w, float thresh, void* cuda_stream);
+/* Blocks until the stream work of the last run finished and results are on the host. */
+int b200pose_post_sync(b200pose_post* post);
+int b200pose_post_num_humans(b200pose_post* post, int img);             /* < 0 on error */
+int b200pose_post_status(b200pose_post* post, int img);                 /* status bits of the last run */
+int b200pose_post_get_humans(b200pose_post* post, int img, float* out, int max_humans);   /* returns count */
+/* joint list rows (x, y, score, id, part), the array paf_to_pose.py:376-378 builds; returns count */
+int b200pose_post_get_peaks(b200pose_post* post, int img, float* out, int max_peaks);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3. Fused path: net forward + post-processing without leaving the device (the batched entry point of
+ *    SURVEY.md 8b).  input: fp32 NCHW [n,3,H,W].
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200pose_infer(b200pose_net* net, b200pose_post* post, const float* input, int input_on_device, int n, int H, int W,
+                   int mode, float thresh, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 4. Legacy SWIG surface of lib/pafprocess (pafprocess.h:53-59, pafprocess.i:14): same names, same argument
+ *    meaning; state is kept in a process-global context exactly like the reference's file-scope globals
+ *    (pafprocess.cpp:12-13).  peaks [p1,p2,5] rows (x, y, score, id, part) sorted by part as paf_to_pose_cpp
+ *    builds them; heatmap is not dereferenced (only h1 is used, pafprocess.cpp:83); pafmap [f1,f2,f3] is the
+ *    x8 nearest-upsampled HWC array.  process_paf returns 0 like the reference, or a non-zero code if the
+ *    device path failed (the reference has no failure mode).
+ * ---------------------------------------------------------------------------------------------------------- */
+int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, float* heatmap, int f1, int f2, int f3,
+                float* pafmap);
+int get_num_humans(void);
+int get_part_cid(int human_id, int part_id);
+float get_score(int human_id);
+int get_part_x(int cid);
+int get_part_y(int cid);
+float get_part_score(int cid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

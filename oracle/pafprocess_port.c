@@ -6,9 +6,7 @@
  * (flat arrays, alive flags instead of vector::erase).  Pinned against the compiled, unmodified reference
  * source (oracle/_ref/libpafprocess_ref.so, built by oracle/Makefile) in tests/test_oracle_pafprocess.py.
  *
- * One deliberate, documented difference: the reference sorts candidates with std::sort (unstable,
- * pafprocess.cpp:97), so the relative order of candidates with EXACTLY equal score is unspecified there;
- * here equal scores keep (idx1, idx2) lexicographic order.
+ * std::sort's handling of exactly-equal scores is reproduced by restating libstdc++'s introsort (see below).
  *
  * Build: gcc -O2 -ffp-contract=off -shared -fPIC pafprocess_port.c -o libpafprocess_port.so -lm
  */
@@ -42,13 +40,103 @@ static int g_nrows = 0;
 static Peak* g_line = NULL;
 static int g_nline = 0;
 
-static int cand_cmp(const void* a, const void* b) {
-    const Cand* x = (const Cand*)a;
-    const Cand* y = (const Cand*)b;
-    if (x->score > y->score) return -1;
-    if (x->score < y->score) return 1;
-    if (x->idx1 != y->idx1) return x->idx1 < y->idx1 ? -1 : 1;
-    return x->idx2 < y->idx2 ? -1 : (x->idx2 > y->idx2);
+/* std::sort(candidates.begin(), candidates.end(), comp_candidate) (pafprocess.cpp:97, comp = a.score > b.score).
+ * The order of candidates with EXACTLY equal score is whatever the standard library's algorithm leaves; such
+ * ties occur in practice (two heat-map peaks refined to the same pixel), so the published libstdc++ algorithm
+ * (bits/stl_algo.h: __introsort_loop, median-of-3 __unguarded_partition_pivot, threshold 16,
+ * __final_insertion_sort; heap-sort fallback when the depth limit 2*floor(log2 n) is exhausted) is restated. */
+#define COMP(a, b) ((a).score > (b).score)
+static void swap_c(Cand* a, Cand* b) { Cand t = *a; *a = *b; *b = t; }
+static void unguarded_linear_insert(Cand* last) {
+    Cand val = *last;
+    Cand* next = last - 1;
+    while (COMP(val, *next)) { *last = *next; last = next; --next; }
+    *last = val;
+}
+static void insertion_sort(Cand* first, Cand* last) {
+    if (first == last) return;
+    for (Cand* i = first + 1; i != last; ++i) {
+        if (COMP(*i, *first)) {
+            Cand val = *i;
+            memmove(first + 1, first, (size_t)(i - first) * sizeof(Cand));
+            *first = val;
+        } else
+            unguarded_linear_insert(i);
+    }
+}
+static void adjust_heap(Cand* first, long hole, long len, Cand value) {   /* std::__adjust_heap + __push_heap */
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (COMP(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;
+    while (hole > top && COMP(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+static void heap_sort(Cand* first, Cand* last) {   /* std::__partial_sort(first, last, last) */
+    const long len = last - first;
+    if (len >= 2)
+        for (long parent = (len - 2) / 2;; --parent) {
+            adjust_heap(first, parent, len, first[parent]);
+            if (parent == 0) break;
+        }
+    while (last - first > 1) {
+        --last;
+        Cand value = *last;
+        *last = *first;
+        adjust_heap(first, 0, last - first, value);
+    }
+}
+static void introsort_loop(Cand* first, Cand* last, int depth_limit) {
+    while (last - first > 16) {
+        if (depth_limit == 0) { heap_sort(first, last); return; }
+        --depth_limit;
+        Cand* mid = first + (last - first) / 2;
+        Cand *a = first + 1, *b = mid, *c = last - 1;   /* __move_median_to_first(first, a, b, c) */
+        if (COMP(*a, *b)) {
+            if (COMP(*b, *c)) swap_c(first, b);
+            else if (COMP(*a, *c)) swap_c(first, c);
+            else swap_c(first, a);
+        } else if (COMP(*a, *c)) swap_c(first, a);
+        else if (COMP(*b, *c)) swap_c(first, c);
+        else swap_c(first, b);
+        Cand *lo = first + 1, *hi = last;               /* __unguarded_partition(first+1, last, pivot=first) */
+        for (;;) {
+            while (COMP(*lo, *first)) ++lo;
+            --hi;
+            while (COMP(*first, *hi)) --hi;
+            if (!(lo < hi)) break;
+            swap_c(lo, hi);
+            ++lo;
+        }
+        introsort_loop(lo, last, depth_limit);
+        last = lo;
+    }
+}
+static void std_sort_desc(Cand* first, int n) {
+    if (n <= 0) return;
+    Cand* last = first + n;
+    int lg = 0;
+    for (int m = n; m > 1; m >>= 1) ++lg;
+    introsort_loop(first, last, 2 * lg);
+    if (n > 16) {
+        insertion_sort(first, first + 16);
+        for (Cand* i = first + 16; i != last; ++i) unguarded_linear_insert(i);
+    } else
+        insertion_sort(first, last);
 }
 
 int port_process_paf(int p1, int p2, int p3, const float* peaks, int h1, int h2, int h3, const float* heatmap, int f1,
@@ -118,7 +206,7 @@ int port_process_paf(int p1, int p2, int p3, const float* peaks, int h1, int h2,
                     ++nc;
                 }
             }
-        qsort(cands, nc, sizeof(Cand), cand_cmp);                  /* :97 */
+        std_sort_desc(cands, nc);                                  /* :97 */
         conns[l] = (Conn*)malloc(sizeof(Conn) * (size_t)(na < nb ? na : nb));
         char* used_a = (char*)calloc(na, 1);
         char* used_b = (char*)calloc(nb, 1);

@@ -1,0 +1,82 @@
+"""ctypes binding of libb200pose.so (include/b200pose.h).  Loading is lazy; every failure is loud."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200pose.so")
+_lib = None
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+NUM_TENSORS = 184
+HUMAN_FLOATS = 73
+MODE_BF16, MODE_FP32 = 0, 1
+MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32}
+
+
+class B200PoseError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200PoseError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU/PyTorch fallback for this path)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cl, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+    sig = {
+        "b200pose_last_error": ([], ctypes.c_char_p),
+        "b200pose_version": ([], ci),
+        "b200pose_launch_count": ([], cl),
+        "b200pose_net_create": ([ctypes.POINTER(vp), ci], ci),
+        "b200pose_net_destroy": ([vp], None),
+        "b200pose_net_tensor_shape": ([ci, ctypes.POINTER(cl)], ci),
+        "b200pose_net_set_tensor": ([vp, ci, vp, cl], ci),
+        "b200pose_net_finalize": ([vp], ci),
+        "b200pose_net_forward": ([vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(vp), ci, vp], ci),
+        "b200pose_net_profile": ([vp, vp, vp, ci, vp], ci),
+        "b200pose_net_last_maps": ([vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ci), ctypes.POINTER(ci),
+                                    ctypes.POINTER(ci)], ci),
+        "b200pose_post_create": ([ctypes.POINTER(vp), ci, ci, ci, ci], ci),
+        "b200pose_post_destroy": ([vp], None),
+        "b200pose_post_run": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
+        "b200pose_post_sync": ([vp], ci),
+        "b200pose_post_num_humans": ([vp, ci], ci),
+        "b200pose_post_status": ([vp, ci], ci),
+        "b200pose_post_get_humans": ([vp, ci, vp, ci], ci),
+        "b200pose_post_get_peaks": ([vp, ci, vp, ci], ci),
+        "b200pose_infer": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
+        "process_paf": ([ci, ci, ci, vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
+        "get_num_humans": ([], ci),
+        "get_part_cid": ([ci, ci], ci),
+        "get_score": ([ci], cf),
+        "get_part_x": ([ci], ci),
+        "get_part_y": ([ci], ci),
+        "get_part_score": ([ci], cf),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)     # AttributeError here = the library does not export what include/b200pose.h declares
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+EXPORTED = ["b200pose_last_error", "b200pose_version", "b200pose_launch_count", "b200pose_net_create",
+            "b200pose_net_destroy", "b200pose_net_tensor_shape", "b200pose_net_set_tensor", "b200pose_net_finalize",
+            "b200pose_net_forward", "b200pose_net_profile", "b200pose_net_last_maps", "b200pose_post_create", "b200pose_post_destroy",
+            "b200pose_post_run", "b200pose_post_sync", "b200pose_post_num_humans", "b200pose_post_status",
+            "b200pose_post_get_humans", "b200pose_post_get_peaks", "b200pose_infer", "process_paf", "get_num_humans",
+            "get_part_cid", "get_score", "get_part_x", "get_part_y", "get_part_score"]
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().b200pose_last_error()
+        raise B200PoseError("%s failed (rc=%d): %s" % (what or "b200pose call", rc, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(lib().b200pose_launch_count())

@@ -1,0 +1,716 @@
+// C-ABI of libb200pose.so (include/b200pose.h): network object, post-processing object, fused inference and the
+// legacy pafprocess surface.  Host-side runtime only; the kernels live in conv_tc.cu, conv_misc.cu, postprocess.cu.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200pose.h"
+#include "conv_misc.cuh"
+#include "conv_tc.cuh"
+#include "postprocess.cuh"
+
+using namespace b2p;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long> g_launches{0};
+
+int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CU(x)                                                                                       \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------- layer table (rtpose_vgg.py:69-127)
+struct ConvSpec { int cin, cout, ks; };
+const ConvSpec kTrunk[12] = {{3, 64, 3},    {64, 64, 3},   {64, 128, 3},  {128, 128, 3}, {128, 256, 3}, {256, 256, 3},
+                             {256, 256, 3}, {256, 256, 3}, {256, 512, 3}, {512, 512, 3}, {512, 256, 3}, {256, 128, 3}};
+const bool kPoolAfter[12] = {false, true, false, true, false, false, false, true, false, false, false, false};
+constexpr int kPaf = 38, kHeat = 19, kFeat = 128, kCat = kPaf + kHeat + kFeat;
+
+int stage_num_layers(int stage) { return stage == 1 ? 5 : 7; }
+ConvSpec stage_layer(int stage, int branch, int li) {
+    const int outc = branch == 0 ? kPaf : kHeat;
+    if (stage == 1) {
+        if (li < 3) return {128, 128, 3};
+        if (li == 3) return {128, 512, 1};
+        return {512, outc, 1};
+    }
+    if (li == 0) return {kCat, 128, 7};
+    if (li < 5) return {128, 128, 7};
+    if (li == 5) return {128, 128, 1};
+    return {128, outc, 1};
+}
+// conv index in state_dict order: trunk 0..11, then branch 0 stages 1..6, then branch 1 stages 1..6
+int conv_index(int stage, int branch, int li) {
+    int idx = 12;
+    for (int b = 0; b < 2; ++b)
+        for (int s = 1; s <= 6; ++s) {
+            if (b == branch && s == stage) return idx + li;
+            idx += stage_num_layers(s);
+        }
+    return -1;
+}
+constexpr int kNumConvs = 12 + 2 * (5 + 5 * 7);   // 92
+ConvSpec conv_spec(int ci) {
+    if (ci < 12) return kTrunk[ci];
+    int idx = 12;
+    for (int b = 0; b < 2; ++b)
+        for (int s = 1; s <= 6; ++s) {
+            const int nl = stage_num_layers(s);
+            if (ci < idx + nl) return stage_layer(s, b, ci - idx);
+            idx += nl;
+        }
+    return {0, 0, 0};
+}
+// physical channel of the bf16 concat buffer [paf 0..37, pad, heat 40..58, pad, feat 64..191] for reference
+// concat channel c of torch.cat([paf, heat, feat], 1) (rtpose_vgg.py:165)
+int cat_phys(int c) { return c < kPaf ? c : (c < kPaf + kHeat ? c + 2 : c + 7); }
+
+uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct TcLayer {            // one grouped tensor-core launch
+    int ks, cin_blocks, groups, n_tile, n_tiles, relu, pool;
+    double macs_per_pixel = 0;    // algorithmic (unpadded) MACs per output pixel, all groups
+    __nv_bfloat16* w = nullptr;   // [taps][groups*n_tiles*n_tile][cin_blocks*64]
+    float* bias = nullptr;        // [groups*n_tiles*n_tile]
+};
+
+}  // namespace
+
+struct b200pose_net {
+    int device = 0, num_sms = 148;
+    bool finalized = false;
+    std::vector<std::vector<float>> host_w, host_b;   // per conv
+    std::vector<bool> have;                            // per tensor
+    float* d_w[kNumConvs] = {};                        // fp32 OIHW (parity mode, conv1_1)
+    float* d_b[kNumConvs] = {};
+    // tensor-core layers: trunk 1..11 -> tc[0..10]; stage 1: tc[11..15]; stage t>=2: tc[16 + (t-2)*7 + li]
+    std::vector<TcLayer> tc;
+    // ---- plan (depends on n, H, W)
+    int pn = 0, pH = 0, pW = 0, pmode = -1;
+    std::vector<ConvTcArgs> plan;
+    std::vector<double> plan_flops;   // algorithmic FLOPs per launch of `plan`
+    DevBuf<__nv_bfloat16> t1, t2, t3, t4, t5a, t5b, t6, t7, t8, t9, cat, bra, brb, br512;
+    DevBuf<float> in_stage, out_f32[12];
+    // fp32 parity buffers
+    DevBuf<float> f_a, f_b, f_cat, f_x, f_y, f_in;
+    cudaStream_t own_stream = nullptr;
+    const float* last_in = nullptr;   // device pointer of the last forward's input (profiling hook)
+};
+
+struct b200pose_post {
+    int device = 0;
+    PostBuffers pb{};
+    DevBuf<float> d_heat, d_paf;
+    std::vector<int> h_nh, h_status, h_counts;
+    std::vector<float> h_humans, h_px_s;
+    std::vector<int> h_px, h_py;
+    int last_n = 0, hw_h = 0, hw_w = 0;
+    bool fetched = false;
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
+namespace {
+
+int pack_tc_layer(b200pose_net* net, TcLayer& L, const std::vector<int>& conv_ids /*per group*/, int n_tile,
+                  bool cat_input, int ks, int relu, int pool) {
+    const int groups = (int)conv_ids.size();
+    const ConvSpec sp = conv_spec(conv_ids[0]);
+    const int cin_pad = cat_input ? 192 : sp.cin;
+    const int cout_pad = ((sp.cout + n_tile - 1) / n_tile) * n_tile;
+    L.ks = ks; L.cin_blocks = cin_pad / 64; L.groups = groups; L.n_tile = n_tile; L.n_tiles = cout_pad / n_tile;
+    L.relu = relu; L.pool = pool;
+    const int taps = ks * ks, rows = groups * cout_pad;
+    L.macs_per_pixel = 0;
+    for (int g = 0; g < groups; ++g) L.macs_per_pixel += (double)conv_spec(conv_ids[g]).cin * conv_spec(conv_ids[g]).cout * taps;
+    std::vector<uint16_t> w((size_t)taps * rows * cin_pad, 0);
+    std::vector<float> b((size_t)rows, 0.f);
+    for (int g = 0; g < groups; ++g) {
+        const ConvSpec s = conv_spec(conv_ids[g]);
+        const std::vector<float>& hw = net->host_w[conv_ids[g]];
+        const std::vector<float>& hb = net->host_b[conv_ids[g]];
+        for (int o = 0; o < s.cout; ++o) {
+            b[g * cout_pad + o] = hb[o];
+            for (int c = 0; c < s.cin; ++c) {
+                const int pc = cat_input ? cat_phys(c) : c;
+                for (int t = 0; t < taps; ++t)
+                    w[((size_t)t * rows + g * cout_pad + o) * cin_pad + pc] = f2bf(hw[((size_t)o * s.cin + c) * taps + t]);
+            }
+        }
+    }
+    CU(cudaMalloc(&L.w, w.size() * 2));
+    CU(cudaMalloc(&L.bias, b.size() * 4));
+    CU(cudaMemcpy(L.w, w.data(), w.size() * 2, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(L.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __nv_bfloat16* in, int in_cstride,
+             int in_ch_base, int in_group_stride, __nv_bfloat16* out, int out_cstride, int off0, int off1, int store0,
+             int store1, float* f32_0, float* f32_1, int f32c0, int f32c1) {
+    ConvTcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_img = n; a.H = H; a.W = W; a.ksize = L.ks; a.cin_blocks = L.cin_blocks;
+    a.in_ch_base = in_ch_base; a.in_ch_group_stride = in_group_stride; a.groups = L.groups;
+    a.n_tile = L.n_tile; a.n_tiles = L.n_tiles; a.bias = L.bias; a.relu = L.relu; a.pool = L.pool;
+    a.out = out; a.out_cstride = out_cstride;
+    a.out_ch_off[0] = off0; a.out_ch_off[1] = off1;
+    a.store_ch[0] = store0; a.store_ch[1] = store1;
+    a.out_f32[0] = f32_0; a.out_f32[1] = f32_1;
+    a.f32_ch[0] = f32c0; a.f32_ch[1] = f32c1;
+    a.use_base_offset = 0;
+    cudaError_t e = conv_tc_make_maps(a, in, in_cstride, L.w);
+    if (e != cudaSuccess) return fail("conv_tc_make_maps failed: %s", cudaGetErrorString(e));
+    net->plan.push_back(a);
+    net->plan_flops.push_back(2.0 * n * H * W * L.macs_per_pixel);
+    return 0;
+}
+
+int build_plan_bf16(b200pose_net* net, int n, int H, int W) {
+    const size_t px1 = (size_t)n * H * W, px2 = px1 / 4, px4 = px1 / 16, px8 = px1 / 64;
+    const int h = H / 8, w = W / 8;
+    CU(net->t1.ensure(px1 * 64)); CU(net->t2.ensure(px2 * 64)); CU(net->t3.ensure(px2 * 128));
+    CU(net->t4.ensure(px4 * 128)); CU(net->t5a.ensure(px4 * 256)); CU(net->t5b.ensure(px4 * 256));
+    CU(net->t6.ensure(px8 * 256)); CU(net->t7.ensure(px8 * 512)); CU(net->t8.ensure(px8 * 512));
+    CU(net->t9.ensure(px8 * 256)); CU(net->cat.ensure(px8 * 192)); CU(net->bra.ensure(px8 * 256));
+    CU(net->brb.ensure(px8 * 256)); CU(net->br512.ensure(px8 * 1024));
+    CU(cudaMemset(net->cat.p, 0, px8 * 192 * 2));
+    for (int i = 0; i < 12; ++i) CU(net->out_f32[i].ensure(px8 * (i % 2 == 0 ? kPaf : kHeat)));
+    net->plan.clear();
+    net->plan_flops.clear();
+    const std::vector<TcLayer>& T = net->tc;
+#define PLAN(...) do { if (add_plan(net, __VA_ARGS__)) return 1; } while (0)
+    // trunk (conv1_1 runs on CUDA cores before the plan)
+    PLAN(T[0], n, H, W, net->t1.p, 64, 0, 0, net->t2.p, 64, 0, 0, 64, 0, nullptr, nullptr, 0, 0);              // conv1_2+pool
+    PLAN(T[1], n, H / 2, W / 2, net->t2.p, 64, 0, 0, net->t3.p, 128, 0, 0, 128, 0, nullptr, nullptr, 0, 0);    // conv2_1
+    PLAN(T[2], n, H / 2, W / 2, net->t3.p, 128, 0, 0, net->t4.p, 128, 0, 0, 128, 0, nullptr, nullptr, 0, 0);   // conv2_2+pool
+    PLAN(T[3], n, H / 4, W / 4, net->t4.p, 128, 0, 0, net->t5a.p, 256, 0, 0, 128, 0, nullptr, nullptr, 0, 0);  // conv3_1
+    PLAN(T[4], n, H / 4, W / 4, net->t5a.p, 256, 0, 0, net->t5b.p, 256, 0, 0, 128, 0, nullptr, nullptr, 0, 0); // conv3_2
+    PLAN(T[5], n, H / 4, W / 4, net->t5b.p, 256, 0, 0, net->t5a.p, 256, 0, 0, 128, 0, nullptr, nullptr, 0, 0); // conv3_3
+    PLAN(T[6], n, H / 4, W / 4, net->t5a.p, 256, 0, 0, net->t6.p, 256, 0, 0, 128, 0, nullptr, nullptr, 0, 0);  // conv3_4+pool
+    PLAN(T[7], n, h, w, net->t6.p, 256, 0, 0, net->t7.p, 512, 0, 0, 128, 0, nullptr, nullptr, 0, 0);            // conv4_1
+    PLAN(T[8], n, h, w, net->t7.p, 512, 0, 0, net->t8.p, 512, 0, 0, 128, 0, nullptr, nullptr, 0, 0);            // conv4_2
+    PLAN(T[9], n, h, w, net->t8.p, 512, 0, 0, net->t9.p, 256, 0, 0, 128, 0, nullptr, nullptr, 0, 0);            // conv4_3_CPM
+    PLAN(T[10], n, h, w, net->t9.p, 256, 0, 0, net->cat.p, 192, 64, 0, 128, 0, nullptr, nullptr, 0, 0);         // conv4_4_CPM -> feat slice
+    // stage 1 (both branches grouped)
+    PLAN(T[11], n, h, w, net->cat.p, 192, 64, 0, net->bra.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+    PLAN(T[12], n, h, w, net->bra.p, 256, 0, 128, net->brb.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+    PLAN(T[13], n, h, w, net->brb.p, 256, 0, 128, net->bra.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+    PLAN(T[14], n, h, w, net->bra.p, 256, 0, 128, net->br512.p, 1024, 0, 512, 128, 128, nullptr, nullptr, 0, 0);
+    PLAN(T[15], n, h, w, net->br512.p, 1024, 0, 512, net->cat.p, 192, 0, 40, 40, 24, net->out_f32[0].p,
+         net->out_f32[1].p, kPaf, kHeat);
+    for (int s = 2; s <= 6; ++s) {
+        const int b0 = 16 + (s - 2) * 7;
+        PLAN(T[b0 + 0], n, h, w, net->cat.p, 192, 0, 0, net->bra.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+        PLAN(T[b0 + 1], n, h, w, net->bra.p, 256, 0, 128, net->brb.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+        PLAN(T[b0 + 2], n, h, w, net->brb.p, 256, 0, 128, net->bra.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+        PLAN(T[b0 + 3], n, h, w, net->bra.p, 256, 0, 128, net->brb.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+        PLAN(T[b0 + 4], n, h, w, net->brb.p, 256, 0, 128, net->bra.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+        PLAN(T[b0 + 5], n, h, w, net->bra.p, 256, 0, 128, net->brb.p, 256, 0, 128, 128, 128, nullptr, nullptr, 0, 0);
+        PLAN(T[b0 + 6], n, h, w, net->brb.p, 256, 0, 128, net->cat.p, 192, 0, 40, 40, 24,
+             net->out_f32[2 * (s - 1)].p, net->out_f32[2 * (s - 1) + 1].p, kPaf, kHeat);
+    }
+#undef PLAN
+    return 0;
+}
+
+int forward_bf16(b200pose_net* net, const float* d_in, int n, int H, int W, cudaStream_t st) {
+    if (net->pn != n || net->pH != H || net->pW != W || net->pmode != B200POSE_MODE_BF16) {
+        CU(cudaStreamSynchronize(st));
+        if (build_plan_bf16(net, n, H, W)) return 1;
+        net->pn = n; net->pH = H; net->pW = W; net->pmode = B200POSE_MODE_BF16;
+    }
+    CU(conv_first_launch(d_in, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st));
+    ++g_launches;
+    for (const ConvTcArgs& a : net->plan) {
+        CU(conv_tc_launch(a, net->num_sms, st));
+        ++g_launches;
+    }
+    return 0;
+}
+
+int forward_fp32(b200pose_net* net, const float* d_in, int n, int H, int W, cudaStream_t st) {
+    const size_t px1 = (size_t)n * H * W;
+    const int h = H / 8, w = W / 8;
+    const size_t px8 = (size_t)n * h * w;
+    CU(net->f_in.ensure(px1 * 3));
+    CU(net->f_a.ensure(px1 * 64)); CU(net->f_b.ensure(px1 * 64));
+    CU(net->f_cat.ensure(px8 * kCat)); CU(net->f_x.ensure(px8 * 512)); CU(net->f_y.ensure(px8 * 512));
+    for (int i = 0; i < 12; ++i) CU(net->out_f32[i].ensure(px8 * (i % 2 == 0 ? kPaf : kHeat)));
+    net->pmode = B200POSE_MODE_FP32;   // invalidates the bf16 plan's claim on out_f32 (same buffers, same sizes)
+    CU(nchw_to_nhwc_f32_launch(d_in, net->f_in.p, n, 3, H, W, 3, 0, st));
+    ++g_launches;
+    const float* cur = net->f_in.p;
+    int cur_c = 3, ch = H, cw = W;
+    float* ping = net->f_a.p;
+    float* pong = net->f_b.p;
+    auto conv = [&](int ci, const float* in, int in_cs, int in_off, float* out, int out_cs, int out_off, int hh, int ww,
+                    int relu, float* nchw) -> int {
+        const ConvSpec s = conv_spec(ci);
+        ConvF32Args a;
+        a.in = in; a.in_cstride = in_cs; a.in_ch_off = in_off; a.w = net->d_w[ci]; a.bias = net->d_b[ci];
+        a.out = out; a.out_cstride = out_cs; a.out_ch_off = out_off; a.out_nchw = nchw;
+        a.n_img = n; a.H = hh; a.W = ww; a.cin = s.cin; a.cout = s.cout; a.ks = s.ks; a.relu = relu;
+        CU(conv_f32_launch(a, st));
+        ++g_launches;
+        return 0;
+    };
+    for (int i = 0; i < 12; ++i) {
+        const ConvSpec s = kTrunk[i];
+        const bool last = (i == 11);
+        float* dst = last ? net->f_cat.p : ping;
+        if (conv(i, cur, cur_c, 0, dst, last ? kCat : s.cout, last ? kPaf + kHeat : 0, ch, cw, 1, nullptr)) return 1;
+        cur = dst; cur_c = s.cout;
+        std::swap(ping, pong);
+        if (kPoolAfter[i]) {
+            CU(maxpool_f32_launch(cur, ping, n, ch, cw, cur_c, st));
+            ++g_launches;
+            cur = ping; ch /= 2; cw /= 2;
+            std::swap(ping, pong);
+        }
+    }
+    for (int s = 1; s <= 6; ++s)
+        for (int b = 0; b < 2; ++b) {
+            const int nl = stage_num_layers(s);
+            const float* in = net->f_cat.p;
+            int in_cs = kCat, in_off = (s == 1) ? kPaf + kHeat : 0;
+            float* bufs[2] = {net->f_x.p, net->f_y.p};
+            for (int li = 0; li < nl; ++li) {
+                const ConvSpec sp = stage_layer(s, b, li);
+                const bool lastl = (li == nl - 1);
+                float* nchw = lastl ? net->out_f32[2 * (s - 1) + b].p : nullptr;
+                // last layer output goes to a scratch slice; the concat for the next stage is written after both
+                // branches are done (the other branch still reads f_cat)
+                float* dst = bufs[li & 1];
+                if (conv(conv_index(s, b, li), in, in_cs, in_off, dst, sp.cout, 0, h, w, lastl ? 0 : 1, nchw)) return 1;
+                in = dst; in_cs = sp.cout; in_off = 0;
+            }
+            if (b == 1 && s < 6) {
+                CU(nchw_to_nhwc_f32_launch(net->out_f32[2 * (s - 1)].p, net->f_cat.p, n, kPaf, h, w, kCat, 0, st));
+                CU(nchw_to_nhwc_f32_launch(net->out_f32[2 * (s - 1) + 1].p, net->f_cat.p, n, kHeat, h, w, kCat, kPaf, st));
+                g_launches += 2;
+            }
+        }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200pose_last_error(void) { return g_err.c_str(); }
+int b200pose_version(void) { return 100; }
+long b200pose_launch_count(void) { return g_launches.load(); }
+
+int b200pose_net_tensor_shape(int index, long dims[4]) {
+    if (index < 0 || index >= B200POSE_NUM_TENSORS) return -1;
+    const ConvSpec s = conv_spec(index / 2);
+    if (index % 2 == 0) { dims[0] = s.cout; dims[1] = s.cin; dims[2] = s.ks; dims[3] = s.ks; return 4; }
+    dims[0] = s.cout;
+    return 1;
+}
+
+int b200pose_net_create(b200pose_net** out, int cuda_device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("b200pose: no CUDA device available (this library has no CPU fallback)");
+    CU(cudaSetDevice(cuda_device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cuda_device));
+    if (prop.major != 10) return fail("b200pose: built for sm_100a (B200); device is sm_%d%d", prop.major, prop.minor);
+    b200pose_net* net = new b200pose_net();
+    net->device = cuda_device;
+    net->num_sms = prop.multiProcessorCount;
+    net->host_w.resize(kNumConvs);
+    net->host_b.resize(kNumConvs);
+    net->have.assign(B200POSE_NUM_TENSORS, false);
+    *out = net;
+    return 0;
+}
+
+void b200pose_net_destroy(b200pose_net* net) {
+    if (!net) return;
+    cudaSetDevice(net->device);
+    for (int i = 0; i < kNumConvs; ++i) { if (net->d_w[i]) cudaFree(net->d_w[i]); if (net->d_b[i]) cudaFree(net->d_b[i]); }
+    for (TcLayer& L : net->tc) { if (L.w) cudaFree(L.w); if (L.bias) cudaFree(L.bias); }
+    DevBuf<__nv_bfloat16>* bb[] = {&net->t1, &net->t2, &net->t3, &net->t4, &net->t5a, &net->t5b, &net->t6,
+                                   &net->t7, &net->t8, &net->t9, &net->cat, &net->bra, &net->brb, &net->br512};
+    for (auto* b : bb) b->release();
+    DevBuf<float>* fb[] = {&net->in_stage, &net->f_a, &net->f_b, &net->f_cat, &net->f_x, &net->f_y, &net->f_in};
+    for (auto* b : fb) b->release();
+    for (auto& b : net->out_f32) b.release();
+    delete net;
+}
+
+int b200pose_net_set_tensor(b200pose_net* net, int index, const float* host_data, long count) {
+    long dims[4];
+    const int nd = b200pose_net_tensor_shape(index, dims);
+    if (nd < 0) return fail("tensor index %d out of range", index);
+    long expect = 1;
+    for (int i = 0; i < nd; ++i) expect *= dims[i];
+    if (count != expect) return fail("tensor %d: got %ld elements, expected %ld", index, count, expect);
+    std::vector<float>& dst = (index % 2 == 0) ? net->host_w[index / 2] : net->host_b[index / 2];
+    dst.assign(host_data, host_data + count);
+    net->have[index] = true;
+    net->finalized = false;
+    return 0;
+}
+
+int b200pose_net_finalize(b200pose_net* net) {
+    CU(cudaSetDevice(net->device));
+    for (int i = 0; i < B200POSE_NUM_TENSORS; ++i)
+        if (!net->have[i]) return fail("state_dict tensor %d was never set", i);
+    for (int i = 0; i < kNumConvs; ++i) {
+        if (net->d_w[i]) cudaFree(net->d_w[i]);
+        if (net->d_b[i]) cudaFree(net->d_b[i]);
+        CU(cudaMalloc(&net->d_w[i], net->host_w[i].size() * 4));
+        CU(cudaMalloc(&net->d_b[i], net->host_b[i].size() * 4));
+        CU(cudaMemcpy(net->d_w[i], net->host_w[i].data(), net->host_w[i].size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(net->d_b[i], net->host_b[i].data(), net->host_b[i].size() * 4, cudaMemcpyHostToDevice));
+    }
+    for (TcLayer& L : net->tc) { if (L.w) cudaFree(L.w); if (L.bias) cudaFree(L.bias); }
+    net->tc.assign(16 + 5 * 7, TcLayer());
+    for (int i = 1; i < 12; ++i) {
+        const ConvSpec s = kTrunk[i];
+        if (pack_tc_layer(net, net->tc[i - 1], {i}, s.cout < 128 ? s.cout : 128, false, 3, 1, kPoolAfter[i])) return 1;
+    }
+    for (int li = 0; li < 5; ++li) {
+        const ConvSpec s = stage_layer(1, 0, li);
+        if (pack_tc_layer(net, net->tc[11 + li], {conv_index(1, 0, li), conv_index(1, 1, li)}, li == 4 ? 48 : 128, false,
+                          s.ks, li != 4, 0))
+            return 1;
+    }
+    for (int st = 2; st <= 6; ++st)
+        for (int li = 0; li < 7; ++li) {
+            const ConvSpec s = stage_layer(st, 0, li);
+            if (pack_tc_layer(net, net->tc[16 + (st - 2) * 7 + li], {conv_index(st, 0, li), conv_index(st, 1, li)},
+                              li == 6 ? 48 : 128, li == 0, s.ks, li != 6, 0))
+                return 1;
+        }
+    net->pn = net->pH = net->pW = 0;
+    net->pmode = -1;
+    net->finalized = true;
+    return 0;
+}
+
+static int net_forward_impl(b200pose_net* net, const float* input, int input_on_device, int n, int H, int W, int mode,
+                            float* const* outputs, int outputs_on_device, cudaStream_t st, bool sync_host) {
+    if (!net || !net->finalized) return fail("net not finalized");
+    if (n < 1 || H < 8 || W < 8 || (H % 8) || (W % 8)) return fail("input must be [n,3,H,W] with H, W multiples of 8");
+    CU(cudaSetDevice(net->device));
+    const float* d_in = input;
+    if (!input_on_device) {
+        CU(net->in_stage.ensure((size_t)n * 3 * H * W));
+        CU(cudaMemcpyAsync(net->in_stage.p, input, (size_t)n * 3 * H * W * 4, cudaMemcpyHostToDevice, st));
+        d_in = net->in_stage.p;
+    }
+    int rc = (mode == B200POSE_MODE_FP32) ? forward_fp32(net, d_in, n, H, W, st) : forward_bf16(net, d_in, n, H, W, st);
+    if (rc) return rc;
+    net->last_in = d_in;
+    net->pn = n; net->pH = H; net->pW = W;
+    if (outputs) {
+        const size_t px8 = (size_t)n * (H / 8) * (W / 8);
+        for (int i = 0; i < 12; ++i)
+            if (outputs[i])
+                CU(cudaMemcpyAsync(outputs[i], net->out_f32[i].p, px8 * (i % 2 == 0 ? kPaf : kHeat) * 4,
+                                   outputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    }
+    if (sync_host && (!input_on_device || (outputs && !outputs_on_device))) CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200pose_net_forward(b200pose_net* net, const float* input, int input_on_device, int n, int H, int W, int mode,
+                         float* const* outputs, int outputs_on_device, void* cuda_stream) {
+    return net_forward_impl(net, input, input_on_device, n, H, W, mode, outputs, outputs_on_device,
+                            reinterpret_cast<cudaStream_t>(cuda_stream), true);
+}
+
+int b200pose_net_profile(b200pose_net* net, float* ms, double* flops, int cap, void* cuda_stream) {
+    if (!net || net->plan.empty() || net->pmode != B200POSE_MODE_BF16) return -1;
+    if (cudaSetDevice(net->device) != cudaSuccess) return -1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const int n = net->pn, H = net->pH, W = net->pW;
+    const int total = (int)net->plan.size() + 1;
+    if (cap < total) return -1;
+    std::vector<cudaEvent_t> ev(total + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    const float* d_in = net->last_in;
+    DevBuf<float> tmp;
+    if (!d_in) { if (tmp.ensure((size_t)n * 3 * H * W) != cudaSuccess) return -1; cudaMemsetAsync(tmp.p, 0, (size_t)n * 3 * H * W * 4, st); d_in = tmp.p; }
+    cudaEventRecord(ev[0], st);
+    conv_first_launch(d_in, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st);
+    cudaEventRecord(ev[1], st);
+    for (size_t i = 0; i < net->plan.size(); ++i) {
+        conv_tc_launch(net->plan[i], net->num_sms, st);
+        cudaEventRecord(ev[i + 2], st);
+    }
+    g_launches += total;
+    if (cudaStreamSynchronize(st) != cudaSuccess) { fail("profile run failed: %s", cudaGetErrorString(cudaGetLastError())); return -1; }
+    for (int i = 0; i < total; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    flops[0] = 2.0 * n * H * W * 27.0 * 64.0;
+    for (size_t i = 0; i < net->plan.size(); ++i) flops[i + 1] = net->plan_flops[i];
+    for (auto& e : ev) cudaEventDestroy(e);
+    tmp.release();
+    return total;
+}
+
+int b200pose_net_last_maps(b200pose_net* net, const float** paf, const float** heat, int* n, int* h, int* w) {
+    if (!net || net->pn == 0) return fail("no forward has run");
+    *paf = net->out_f32[10].p; *heat = net->out_f32[11].p;
+    *n = net->pn; *h = net->pH / 8; *w = net->pW / 8;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ post
+int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, int peak_cap, int human_cap) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("b200pose: no CUDA device available (this library has no CPU fallback)");
+    CU(cudaSetDevice(cuda_device));
+    b200pose_post* p = new b200pose_post();
+    p->device = cuda_device;
+    const long pool = (long)batch_cap * 19 * 32768 < (1L << 26) ? (long)batch_cap * 19 * 32768 : (1L << 26);
+    cudaError_t e = post_alloc(p->pb, batch_cap, peak_cap, human_cap, pool);
+    if (e != cudaSuccess) { delete p; return fail("post_alloc failed: %s", cudaGetErrorString(e)); }
+    CU(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+    *out = p;
+    return 0;
+}
+
+void b200pose_post_destroy(b200pose_post* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    post_free(p->pb);
+    p->d_heat.release(); p->d_paf.release();
+    if (p->done) cudaEventDestroy(p->done);
+    delete p;
+}
+
+static int post_run_dev(b200pose_post* p, const float* d_heat, const float* d_paf, int layout, int n, int h, int w,
+                        float thresh, cudaStream_t st) {
+    if (n > p->pb.batch_cap) return fail("batch %d exceeds post batch_cap %d", n, p->pb.batch_cap);
+    cudaError_t e;
+    if (layout == 0) {
+        e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, (long)h * w, w, 1, h, w, thresh, st);
+        if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
+        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, (long)h * w, w, 1, 3, h * 8, st);
+    } else {
+        e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, 1, (long)w * 19, 19, h, w, thresh, st);
+        if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
+        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, 1, (long)w * 38, 38, 3, h * 8, st);
+    }
+    if (e != cudaSuccess) return fail("post_limbs_and_assemble: %s", cudaGetErrorString(e));
+    g_launches += 3;
+    p->last_n = n; p->hw_h = h; p->hw_w = w; p->fetched = false; p->last_stream = st;
+    CU(cudaEventRecord(p->done, st));
+    return 0;
+}
+
+int b200pose_post_run(b200pose_post* p, const float* heat, const float* paf, int on_device, int layout, int n, int h,
+                      int w, float thresh, void* cuda_stream) {
+    if (!p) return fail("null post");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const float *dh = heat, *dp = paf;
+    if (!on_device) {
+        CU(p->d_heat.ensure((size_t)n * 19 * h * w));
+        CU(p->d_paf.ensure((size_t)n * 38 * h * w));
+        CU(cudaMemcpyAsync(p->d_heat.p, heat, (size_t)n * 19 * h * w * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(p->d_paf.p, paf, (size_t)n * 38 * h * w * 4, cudaMemcpyHostToDevice, st));
+        dh = p->d_heat.p; dp = p->d_paf.p;
+    }
+    return post_run_dev(p, dh, dp, layout, n, h, w, thresh, st);
+}
+
+int b200pose_post_sync(b200pose_post* p) {
+    if (!p) return fail("null post");
+    if (p->fetched) return 0;
+    CU(cudaSetDevice(p->device));
+    const int n = p->last_n;
+    const PostBuffers& pb = p->pb;
+    cudaStream_t st = p->last_stream;
+    p->h_nh.resize(n); p->h_status.resize(n); p->h_counts.resize((size_t)n * 18);
+    CU(cudaMemcpyAsync(p->h_nh.data(), pb.n_humans, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(p->h_status.data(), pb.status, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(p->h_counts.data(), pb.counts, (size_t)n * 18 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int max_h = 0;
+    for (int i = 0; i < n; ++i) max_h = p->h_nh[i] > max_h ? p->h_nh[i] : max_h;
+    p->h_humans.resize((size_t)n * pb.human_cap * kHumanFloats);
+    for (int i = 0; i < n; ++i)
+        if (p->h_nh[i] > 0)
+            CU(cudaMemcpyAsync(p->h_humans.data() + (size_t)i * pb.human_cap * kHumanFloats,
+                               pb.humans + (size_t)i * pb.human_cap * kHumanFloats,
+                               (size_t)p->h_nh[i] * kHumanFloats * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    p->h_px.clear();   // peaks are fetched lazily by get_peaks
+    p->fetched = true;
+    return 0;
+}
+
+int b200pose_post_num_humans(b200pose_post* p, int img) {
+    if (b200pose_post_sync(p)) return -1;
+    if (img < 0 || img >= p->last_n) return -1;
+    return p->h_nh[img];
+}
+int b200pose_post_status(b200pose_post* p, int img) {
+    if (b200pose_post_sync(p)) return -1;
+    if (img < 0 || img >= p->last_n) return -1;
+    return p->h_status[img];
+}
+int b200pose_post_get_humans(b200pose_post* p, int img, float* out, int max_humans) {
+    if (b200pose_post_sync(p)) return -1;
+    if (img < 0 || img >= p->last_n) return -1;
+    const int n = p->h_nh[img] < max_humans ? p->h_nh[img] : max_humans;
+    memcpy(out, p->h_humans.data() + (size_t)img * p->pb.human_cap * kHumanFloats, (size_t)n * kHumanFloats * sizeof(float));
+    return n;
+}
+int b200pose_post_get_peaks(b200pose_post* p, int img, float* out, int max_peaks) {
+    if (b200pose_post_sync(p)) return -1;
+    if (img < 0 || img >= p->last_n) return -1;
+    const PostBuffers& pb = p->pb;
+    const size_t per = (size_t)18 * pb.peak_cap;
+    if (p->h_px.empty()) {
+        const size_t tot = per * p->last_n;
+        p->h_px.resize(tot); p->h_py.resize(tot); p->h_px_s.resize(tot);
+        if (cudaMemcpy(p->h_px.data(), pb.peak_x, tot * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(p->h_py.data(), pb.peak_y, tot * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(p->h_px_s.data(), pb.peak_s, tot * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            fail("peak copy failed");
+            return -1;
+        }
+    }
+    int k = 0;
+    for (int part = 0; part < 18; ++part) {
+        const int c = p->h_counts[(size_t)img * 18 + part];
+        for (int i = 0; i < c && k < max_peaks; ++i, ++k) {
+            const size_t o = (size_t)img * per + (size_t)part * pb.peak_cap + i;
+            out[5 * k + 0] = (float)p->h_px[o];
+            out[5 * k + 1] = (float)p->h_py[o];
+            out[5 * k + 2] = p->h_px_s[o];
+            out[5 * k + 3] = (float)k;
+            out[5 * k + 4] = (float)part;
+        }
+    }
+    return k;
+}
+
+int b200pose_infer(b200pose_net* net, b200pose_post* post, const float* input, int input_on_device, int n, int H, int W,
+                   int mode, float thresh, void* cuda_stream) {
+    if (!net || !post) return fail("null handle");
+    if (net->device != post->device) return fail("net and post live on different devices");
+    // host input is staged asynchronously: the caller keeps it alive until b200pose_post_sync()
+    int rc = net_forward_impl(net, input, input_on_device, n, H, W, mode, nullptr, 1,
+                              reinterpret_cast<cudaStream_t>(cuda_stream), false);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return post_run_dev(post, net->out_f32[11].p, net->out_f32[10].p, 0, n, H / 8, W / 8, thresh, st);
+}
+
+// ------------------------------------------------------------------------------------------------ legacy pafprocess
+namespace {
+std::mutex g_legacy_mu;
+b200pose_post* g_legacy = nullptr;
+std::vector<float> g_leg_humans;       // [nh][73]
+std::vector<float> g_leg_peaks;        // by id: x, y, score
+int g_leg_nh = 0;
+}  // namespace
+
+int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, float* heatmap, int f1, int f2, int f3,
+                float* pafmap) {
+    (void)h2; (void)h3; (void)heatmap;
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    g_leg_nh = 0;
+    if (p3 != 5) return fail("process_paf: peaks must be [p1,p2,5]");
+    if (f3 != 38) return fail("process_paf: pafmap must have 38 channels");
+    const int P = p1 * p2;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int cap = 2048;
+    if (!g_legacy) {
+        if (b200pose_post_create(&g_legacy, dev, 1, cap, 4096)) return 2;
+    }
+    b200pose_post* p = g_legacy;
+    CU(cudaSetDevice(p->device));
+    // bucket by part (pafprocess.cpp:24-43); ids follow input order, which equals part order for the array
+    // paf_to_pose_cpp builds (we require that order, the reference silently mis-indexes otherwise)
+    std::vector<int> counts(18, 0), hx((size_t)18 * cap), hy((size_t)18 * cap);
+    std::vector<float> hs((size_t)18 * cap);
+    int prev_part = 0;
+    g_leg_peaks.assign((size_t)P * 3, 0.f);
+    for (int i = 0; i < P; ++i) {
+        const float* r = peaks + (size_t)i * 5;
+        const int part = (int)r[4];
+        if (part < 0 || part >= 18) return fail("process_paf: part id %d out of range", part);
+        if (part < prev_part) return fail("process_paf: peaks must be ordered by part");
+        prev_part = part;
+        if (counts[part] >= cap) return fail("process_paf: more than %d peaks for part %d", cap, part);
+        const size_t o = (size_t)part * cap + counts[part]++;
+        hx[o] = (int)r[0]; hy[o] = (int)r[1]; hs[o] = r[2];
+        g_leg_peaks[3 * i] = (float)(int)r[0]; g_leg_peaks[3 * i + 1] = (float)(int)r[1]; g_leg_peaks[3 * i + 2] = r[2];
+    }
+    const PostBuffers& pb = p->pb;
+    cudaStream_t st = nullptr;
+    CU(cudaMemsetAsync(pb.status, 0, sizeof(int), st));
+    CU(cudaMemcpyAsync(pb.counts, counts.data(), 18 * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pb.peak_x, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pb.peak_y, hy.data(), hy.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(pb.peak_s, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(p->d_paf.ensure((size_t)f1 * f2 * f3));
+    CU(cudaMemcpyAsync(p->d_paf.p, pafmap, (size_t)f1 * f2 * f3 * 4, cudaMemcpyHostToDevice, st));
+    cudaError_t e = post_limbs_and_assemble(pb, 1, p->d_paf.p, 0, 1, (long)f2 * f3, f3, 0, h1, st);
+    if (e != cudaSuccess) return fail("post_limbs_and_assemble: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    p->last_n = 1; p->fetched = false; p->last_stream = st;
+    if (b200pose_post_sync(p)) return 3;
+    if (p->h_status[0] & 0xff & ~16) return fail("process_paf: capacity exceeded (status %d)", p->h_status[0]);
+    g_leg_nh = p->h_nh[0];
+    g_leg_humans.assign(p->h_humans.begin(), p->h_humans.begin() + (size_t)g_leg_nh * kHumanFloats);
+    return 0;
+}
+int get_num_humans(void) { return g_leg_nh; }
+int get_part_cid(int human_id, int part_id) { return (int)g_leg_humans[(size_t)human_id * kHumanFloats + 1 + 4 * part_id + 3]; }
+float get_score(int human_id) { return g_leg_humans[(size_t)human_id * kHumanFloats]; }
+int get_part_x(int cid) { return (int)g_leg_peaks[3 * (size_t)cid]; }
+int get_part_y(int cid) { return (int)g_leg_peaks[3 * (size_t)cid + 1]; }
+float get_part_score(int cid) { return g_leg_peaks[3 * (size_t)cid + 2]; }
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// Sequential-exact cores of the fused post-processing, shared between device code (postprocess.cu) and a
+// host-only unit test (tests/cuda/test_post_core.cpp, compiled with g++).  They restate, operation for
+// operation, /root/reference/lib/pafprocess/pafprocess.cpp:
+//   pair_score()      :57-94 + get_paf_vectors :220-238 + roundpaf :240-242
+//   sort_candidates() :97   (std::sort, libstdc++ introsort - reproduces its order for exactly-equal scores)
+//   greedy_match()    :98-124
+//   Assembler         :127-191 (person assembly / merge / prune) with O(1) row lookup instead of a linear scan
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2P_HD __host__ __device__ __forceinline__
+#else
+#define B2P_HD inline
+#include <math.h>
+#endif
+
+namespace b2p {
+
+constexpr int kNumPart = 18;
+constexpr int kNumLimb = 19;
+constexpr int kStepPaf = 10;          // pafprocess.h:13
+constexpr int kRowFloats = 20;        // 18 part ids, [18] score sum, [19] part count
+#define B2P_LIMB_TABLES                                                                                            \
+    { {1, 2}, {1, 5}, {2, 3}, {3, 4}, {5, 6}, {6, 7}, {1, 8}, {8, 9}, {9, 10}, {1, 11}, {11, 12}, {12, 13}, {1, 0}, \
+      {0, 14}, {14, 16}, {0, 15}, {15, 17}, {2, 16}, {5, 17} }
+#define B2P_LIMB_PAF_TABLES                                                                                    \
+    { {12, 13}, {20, 21}, {14, 15}, {16, 17}, {22, 23}, {24, 25}, {0, 1}, {2, 3}, {4, 5}, {6, 7}, {8, 9},     \
+      {10, 11}, {28, 29}, {30, 31}, {34, 35}, {32, 33}, {36, 37}, {18, 19}, {26, 27} }
+
+// ---- exact IEEE single ops (no FMA contraction on either side)
+#if defined(__CUDA_ARCH__)
+B2P_HD float f_mul(float a, float b) { return __fmul_rn(a, b); }
+B2P_HD float f_add(float a, float b) { return __fadd_rn(a, b); }
+B2P_HD float f_div(float a, float b) { return __fdiv_rn(a, b); }
+B2P_HD float f_sqrt(float a) { return __fsqrt_rn(a); }
+#else
+B2P_HD float f_mul(float a, float b) { volatile float r = a * b; return r; }
+B2P_HD float f_add(float a, float b) { volatile float r = a + b; return r; }
+B2P_HD float f_div(float a, float b) { volatile float r = a / b; return r; }
+B2P_HD float f_sqrt(float a) { return sqrtf(a); }
+#endif
+
+// PAF accessor: value of channel c at UPSAMPLED pixel (y, x) = base[c*sc + (y>>shift)*sy + (x>>shift)*sx].
+// shift=3 reads the low-res map in place of the x8 nearest-neighbour copy the reference materialises
+// (paf_to_pose.py:382-383); shift=0 serves the legacy process_paf() call that is handed the upsampled HWC array.
+struct PafView {
+    const float* base;
+    long sc, sy, sx;
+    int shift;
+    B2P_HD float at(int c, int y, int x) const { return base[c * sc + (long)(y >> shift) * sy + (long)(x >> shift) * sx]; }
+};
+
+// Scores one (a, b) peak pair of a limb.  Returns true and the candidate score if it passes both criteria.
+B2P_HD bool pair_score(const PafView& paf, int c1, int c2, int ax, int ay, int bx, int by, int h_up, float* score_out) {
+    const int dxi = bx - ax, dyi = by - ay;
+    float vx = (float)dxi, vy = (float)dyi;
+    const float norm = f_sqrt(f_add(f_mul(vx, vx), f_mul(vy, vy)));
+    if ((double)norm < 1e-12) return false;
+    vx = f_div(vx, norm);
+    vy = f_div(vy, norm);
+    const float step_x = f_div((float)dxi, (float)kStepPaf);
+    const float step_y = f_div((float)dyi, (float)kStepPaf);
+    float scores = 0.0f;
+    int crit1 = 0;
+    for (int i = 0; i < kStepPaf; ++i) {
+        const int lx = (int)((double)f_add((float)ax, f_mul((float)i, step_x)) + 0.5);
+        const int ly = (int)((double)f_add((float)ay, f_mul((float)i, step_y)) + 0.5);
+        const float s = f_add(f_mul(vx, paf.at(c1, ly, lx)), f_mul(vy, paf.at(c2, ly, lx)));
+        scores = f_add(scores, s);
+        if (s > 0.05f) crit1 += 1;
+    }
+    const double pen = 0.5 * h_up / (double)norm - 1.0;
+    const float crit2 = (float)((double)f_div(scores, (float)kStepPaf) + (pen < 0.0 ? pen : 0.0));
+    if (crit1 > 6 && crit2 > 0.f) {
+        *score_out = crit2;
+        return true;
+    }
+    return false;
+}
+
+// Candidate key: high 32 bits = ~bits(score) (score > 0, so ascending key == descending score), low 32 bits =
+// pair index a*nb+b (the order the reference generates candidates in).
+B2P_HD uint64_t cand_key(float score, uint32_t pair) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t b = __float_as_uint(score);
+#else
+    union { float f; uint32_t u; } cv; cv.f = score; const uint32_t b = cv.u;
+#endif
+    return ((uint64_t)(~b) << 32) | pair;
+}
+B2P_HD float key_score(uint64_t k) {
+    const uint32_t b = ~(uint32_t)(k >> 32);
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } cv; cv.u = b; return cv.f;
+#endif
+}
+// comp_candidate(a, b) = a.score > b.score  (pafprocess.cpp:244-246)
+#define B2P_COMP(a, b) ((uint32_t)((a) >> 32) < (uint32_t)((b) >> 32))
+
+// libstdc++ std::sort on keys given in generation order; only needed when equal scores exist (a stable parallel
+// sort gives the same permutation otherwise).  Iterative form of __introsort_loop + __final_insertion_sort.
+B2P_HD void seq_unguarded_linear_insert(uint64_t* v, long last) {
+    const uint64_t val = v[last];
+    long next = last - 1;
+    while (B2P_COMP(val, v[next])) { v[last] = v[next]; last = next; --next; }
+    v[last] = val;
+}
+B2P_HD void seq_insertion_sort(uint64_t* v, long first, long last) {
+    if (first == last) return;
+    for (long i = first + 1; i != last; ++i) {
+        if (B2P_COMP(v[i], v[first])) {
+            const uint64_t val = v[i];
+            for (long j = i; j > first; --j) v[j] = v[j - 1];
+            v[first] = val;
+        } else
+            seq_unguarded_linear_insert(v, i);
+    }
+}
+B2P_HD void seq_adjust_heap(uint64_t* f, long hole, long len, uint64_t value) {
+    const long top = hole;
+    long child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (B2P_COMP(f[child], f[child - 1])) child--;
+        f[hole] = f[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        f[hole] = f[child - 1];
+        hole = child - 1;
+    }
+    long parent = (hole - 1) / 2;
+    while (hole > top && B2P_COMP(f[parent], value)) { f[hole] = f[parent]; hole = parent; parent = (hole - 1) / 2; }
+    f[hole] = value;
+}
+B2P_HD void seq_heap_sort(uint64_t* v, long first, long last) {
+    uint64_t* f = v + first;
+    long len = last - first;
+    if (len >= 2)
+        for (long parent = (len - 2) / 2;; --parent) {
+            seq_adjust_heap(f, parent, len, f[parent]);
+            if (parent == 0) break;
+        }
+    while (len > 1) {
+        --len;
+        const uint64_t value = f[len];
+        f[len] = f[0];
+        seq_adjust_heap(f, 0, len, value);
+    }
+}
+B2P_HD void seq_std_sort(uint64_t* v, int n) {
+    if (n <= 0) return;
+    int lg = 0;
+    for (int m = n; m > 1; m >>= 1) ++lg;
+    // explicit stack replaces the recursion on the right part
+    long st_first[64], st_last[64];
+    int st_depth[64], sp = 0;
+    st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        long first = st_first[sp], last = st_last[sp];
+        int depth = st_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) { seq_heap_sort(v, first, last); break; }
+            --depth;
+            const long mid = first + (last - first) / 2;
+            const long a = first + 1, b = mid, c = last - 1;
+            long m;
+            if (B2P_COMP(v[a], v[b])) m = B2P_COMP(v[b], v[c]) ? b : (B2P_COMP(v[a], v[c]) ? c : a);
+            else m = B2P_COMP(v[a], v[c]) ? a : (B2P_COMP(v[b], v[c]) ? c : b);
+            { const uint64_t t = v[first]; v[first] = v[m]; v[m] = t; }
+            long lo = first + 1, hi = last;
+            for (;;) {
+                while (B2P_COMP(v[lo], v[first])) ++lo;
+                --hi;
+                while (B2P_COMP(v[first], v[hi])) --hi;
+                if (!(lo < hi)) break;
+                const uint64_t t = v[lo]; v[lo] = v[hi]; v[hi] = t;
+                ++lo;
+            }
+            // recurse on [lo, last) first (as libstdc++ does), then loop on [first, lo): order of the two
+            // sub-sorts does not change the result since they touch disjoint ranges.
+            if (sp < 64) { st_first[sp] = lo; st_last[sp] = last; st_depth[sp] = depth; ++sp; }
+            last = lo;
+        }
+    }
+    if (n > 16) {
+        seq_insertion_sort(v, 0, 16);
+        for (long i = 16; i != n; ++i) seq_unguarded_linear_insert(v, i);
+    } else
+        seq_insertion_sort(v, 0, n);
+}
+
+// Greedy one-to-one assignment over sorted candidates.  used_a/used_b: zeroed bitmaps.  Writes accepted
+// connections (a index, b index, score) in acceptance order; returns their number.
+B2P_HD int greedy_match(const uint64_t* keys, int n, int nb, uint32_t* used_a, uint32_t* used_b, int max_conn,
+                        int* conn_a, int* conn_b, float* conn_s) {
+    int nc = 0;
+    for (int i = 0; i < n && nc < max_conn; ++i) {
+        const uint32_t pair = (uint32_t)keys[i];
+        const int a = pair / nb, b = pair % nb;
+        if ((used_a[a >> 5] >> (a & 31)) & 1u) continue;
+        if ((used_b[b >> 5] >> (b & 31)) & 1u) continue;
+        used_a[a >> 5] |= 1u << (a & 31);
+        used_b[b >> 5] |= 1u << (b & 31);
+        conn_a[nc] = a;
+        conn_b[nc] = b;
+        conn_s[nc] = key_score(keys[i]);
+        ++nc;
+    }
+    return nc;
+}
+
+// ---------------------------------------------------------------- person assembly
+// Rows ("subset" in the reference) are float[20].  `rows` has capacity row_cap; erased rows are flagged dead and
+// skipped (= vector::erase order).  For O(1) lookup every peak id keeps the list of alive rows holding it in its
+// own part's slot (capacity kListCap; a longer list flips `degraded`, after which lookups scan all rows).
+constexpr int kListCap = 4;
+
+struct Assembler {
+    float* rows;            // [row_cap][20]
+    uint8_t* alive;         // [row_cap]
+    int32_t* lists;         // [n_peaks][kListCap]
+    uint8_t* list_n;        // [n_peaks]
+    const int* part_base;   // [19] first peak id of each part (prefix sum of counts), [18] = total
+    const float* peak_score;// [n_peaks] by id
+    int row_cap, nrows, degraded, overflow;
+
+    B2P_HD bool valid_id(float v, int part) const {
+        return v >= (float)part_base[part] && v < (float)part_base[part + 1];
+    }
+    B2P_HD void list_add(int id, int r) {
+        int n = list_n[id];
+        if (n >= kListCap) { degraded = 1; return; }
+        lists[id * kListCap + n] = r;
+        list_n[id] = (uint8_t)(n + 1);
+    }
+    B2P_HD void list_remove(int id, int r) {
+        int n = list_n[id];
+        for (int i = 0; i < n; ++i)
+            if (lists[id * kListCap + i] == r) {
+                lists[id * kListCap + i] = lists[id * kListCap + n - 1];
+                list_n[id] = (uint8_t)(n - 1);
+                return;
+            }
+    }
+    B2P_HD void set_slot(int r, int part, float nv) {
+        const float old = rows[r * kRowFloats + part];
+        if (valid_id(old, part)) list_remove((int)old, r);
+        rows[r * kRowFloats + part] = nv;
+        if (valid_id(nv, part)) list_add((int)nv, r);
+    }
+    // rows holding cid1 at p1 or cid2 at p2: count + two lowest row indices
+    B2P_HD void lookup(int p1, int cid1, int p2, int cid2, int* found, int* s1, int* s2) const {
+        int f = 0, a = 0x7fffffff, b = 0x7fffffff;
+        if (!degraded) {
+            for (int pass = 0; pass < 2; ++pass) {
+                const int id = pass ? cid2 : cid1;
+                const int other_p = pass ? p1 : p2;
+                const int other_id = pass ? cid1 : cid2;
+                const int n = list_n[id];
+                for (int i = 0; i < n; ++i) {
+                    const int r = lists[id * kListCap + i];
+                    // a row matching on both slots is counted once (in pass 0)
+                    if (pass == 1 && rows[r * kRowFloats + other_p] == (float)other_id) continue;
+                    ++f;
+                    if (r < a) { b = a; a = r; } else if (r < b) b = r;
+                }
+            }
+        } else {
+            for (int r = 0; r < nrows; ++r) {
+                if (!alive[r]) continue;
+                if (rows[r * kRowFloats + p1] == (float)cid1 || rows[r * kRowFloats + p2] == (float)cid2) {
+                    ++f;
+                    if (r < a) { b = a; a = r; } else if (r < b) b = r;
+                }
+            }
+        }
+        *found = f; *s1 = a; *s2 = b;
+    }
+    // one connection of limb `limb` (parts p1 -> p2), pafprocess.cpp:133-184
+    B2P_HD void add_connection(int limb, int p1, int p2, int cid1, int cid2, float cscore) {
+        int found, s1, s2;
+        lookup(p1, cid1, p2, cid2, &found, &s1, &s2);
+        if (found == 1) {
+            float* r1 = rows + s1 * kRowFloats;
+            if (r1[p2] != (float)cid2) {
+                set_slot(s1, p2, (float)cid2);
+                r1[19] = f_add(r1[19], 1.f);
+                r1[18] = f_add(r1[18], f_add(peak_score[cid2], cscore));
+            }
+        } else if (found == 2) {
+            float* r1 = rows + s1 * kRowFloats;
+            float* r2 = rows + s2 * kRowFloats;
+            int membership = 0;
+            for (int k = 0; k < 18; ++k)
+                if (r1[k] > 0 && r2[k] > 0) membership = 2;
+            if (membership == 0) {
+                for (int k = 0; k < 18; ++k) {
+                    const float nv = f_add(r1[k], f_add(r2[k], 1.f));
+                    if (valid_id(r2[k], k)) list_remove((int)r2[k], s2);
+                    set_slot(s1, k, nv);
+                }
+                r1[19] = f_add(r1[19], r2[19]);
+                r1[18] = f_add(r1[18], r2[18]);
+                r1[18] = f_add(r1[18], cscore);
+                alive[s2] = 0;
+            } else {
+                set_slot(s1, p2, (float)cid2);
+                r1[19] = f_add(r1[19], 1.f);
+                r1[18] = f_add(r1[18], f_add(peak_score[cid2], cscore));
+            }
+        } else if (found == 0 && limb < 18) {
+            if (nrows >= row_cap) { overflow = 1; return; }
+            float* row = rows + nrows * kRowFloats;
+            for (int k = 0; k < kRowFloats; ++k) row[k] = -1.f;
+            alive[nrows] = 1;
+            set_slot(nrows, p1, (float)cid1);
+            set_slot(nrows, p2, (float)cid2);
+            row[19] = 2.f;
+            row[18] = f_add(f_add(peak_score[cid1], peak_score[cid2]), cscore);
+            ++nrows;
+        }
+    }
+    // prune (pafprocess.cpp:187-191): keep rows with count >= 4 and score/count >= 0.3
+    B2P_HD bool keep(int r) const {
+        if (!alive[r]) return false;
+        const float* row = rows + r * kRowFloats;
+        return !(row[19] < 4.f || f_div(row[18], row[19]) < 0.3f);
+    }
+};
+
+}  // namespace b2p

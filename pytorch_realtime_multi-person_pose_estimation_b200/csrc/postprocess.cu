@@ -1,0 +1,433 @@
+// Fused post-processing kernel family for sm_100a: heat-map NMS + bicubic refinement, PAF line-integral scoring
+// + greedy bipartite matching, person assembly.  See postprocess.cuh for the reference lines each kernel replaces.
+// HBM-side this path touches 56 x h x w x 4 B per image once (18 heat + 38 PAF planes); it is latency bound, so
+// the design goal is: everything stays on the device, one block per (image, part) / (image, limb) / image, warp
+// shuffles for ordered compaction and arg-max, shared memory for the plane / candidate keys.
+#include <cstdio>
+
+#include "postprocess.cuh"
+
+namespace b2p {
+
+namespace {
+
+__constant__ int c_limb_parts[kNumLimb][2] = B2P_LIMB_TABLES;
+__constant__ int c_limb_paf[kNumLimb][2] = B2P_LIMB_PAF_TABLES;
+
+// OpenCV interpolateCubic (A = -0.75) for the 8 destination phases of an x8 up-sampling; exact float32 values
+// (the 8 x 4 table is pinned against OpenCV in tests/test_oracle.py).  Phases 0-3 start at tap floor(src)-1 = X/8 - 2, phases 4-7 at X/8 - 1.
+__constant__ float c_cubic[8][4] = {
+    {-0x1.4acp-4f, 0x1.0568p-1f, 0x1.5918p-1f, -0x1.a94p-4f}, {-0x1.9c8p-5f, 0x1.5efp-2f, 0x1.a308p-1f, -0x1.c5cp-4f},
+    {-0x1.5fp-6f, 0x1.7b2p-3f, 0x1.dbb8p-1f, -0x1.7c4p-4f},   {-0x1.68p-9f, 0x1.ad8p-5f, 0x1.fba8p-1f, -0x1.518p-5f},
+    {-0x1.518p-5f, 0x1.fba8p-1f, 0x1.ad8p-5f, -0x1.68p-9f},   {-0x1.7c4p-4f, 0x1.dbb8p-1f, 0x1.7b2p-3f, -0x1.5fp-6f},
+    {-0x1.c5cp-4f, 0x1.a308p-1f, 0x1.5efp-2f, -0x1.9c8p-5f},  {-0x1.a94p-4f, 0x1.5918p-1f, 0x1.0568p-1f, -0x1.4acp-4f}};
+
+constexpr int kPeakThreads = 256;
+constexpr int kLimbThreads = 512;
+constexpr int kAsmThreads = 128;
+constexpr int kHorStride = 40;   // (2*2+1) * 8
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ------------------------------------------------------------------ peaks
+__global__ void __launch_bounds__(kPeakThreads) peaks_kernel(PostBuffers pb, const float* __restrict__ heat, long h_img,
+                                                             long h_ch, long h_y, long h_x, int h, int w, float thresh) {
+    extern __shared__ float sm_f[];
+    float* plane = sm_f;                       // [h*w]
+    float* hor_all = sm_f + h * w;             // [8 warps][5][40]
+    __shared__ int warp_cnt[kPeakThreads / 32];
+    __shared__ int s_base;
+    const int part = blockIdx.x, img = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hw = h * w;
+    const float* src = heat + img * h_img + part * h_ch;
+    for (int i = tid; i < hw; i += kPeakThreads) plane[i] = src[(long)(i / w) * h_y + (long)(i % w) * h_x];
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+
+    const int cap = pb.peak_cap;
+    int* px = pb.peak_x + ((long)img * kNumPart + part) * cap;
+    int* py = pb.peak_y + ((long)img * kNumPart + part) * cap;
+    float* ps = pb.peak_s + ((long)img * kNumPart + part) * cap;
+
+    // find_peaks: ordered (raster) compaction
+    for (int start = 0; start < hw; start += kPeakThreads) {
+        const int i = start + tid;
+        bool flag = false;
+        int x = 0, y = 0;
+        if (i < hw) {
+            y = i / w;
+            x = i - y * w;
+            const float v = plane[i];
+            flag = (v > thresh) && (y == 0 || v >= plane[i - w]) && (y == h - 1 || v >= plane[i + w]) &&
+                   (x == 0 || v >= plane[i - 1]) && (x == w - 1 || v >= plane[i + 1]);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int pre = s_base, tot = 0;
+        for (int k = 0; k < kPeakThreads / 32; ++k) {
+            if (k < warp) pre += warp_cnt[k];
+            tot += warp_cnt[k];
+        }
+        const int pos = pre + __popc(m & ((1u << lane) - 1u));
+        if (flag && pos < cap) {
+            px[pos] = x;
+            py[pos] = y;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += tot;
+        __syncthreads();
+    }
+    int n = s_base;
+    if (n > cap) {
+        if (tid == 0) atomicOr(&pb.status[img], 1);
+        n = cap;
+    }
+    if (tid == 0) pb.counts[img * kNumPart + part] = n;
+
+    // refinement: 5x5 window (clipped) -> x8 bicubic -> first arg-max        (one warp per peak)
+    float* hor = hor_all + warp * 5 * kHorStride;
+    for (int pk = warp; pk < n; pk += kPeakThreads / 32) {
+        const int x = px[pk], y = py[pk];
+        const int x_min = max(0, x - 2), x_max = min(w - 1, x + 2);
+        const int y_min = max(0, y - 2), y_max = min(h - 1, y + 2);
+        const int pw = x_max - x_min + 1, ph = y_max - y_min + 1;
+        const int W8 = pw * 8, H8 = ph * 8;
+        __syncwarp();
+        for (int idx = lane; idx < ph * W8; idx += 32) {
+            const int r = idx / W8, X = idx - r * W8;
+            const int phase = X & 7;
+            const int sx = (X >> 3) + (phase < 4 ? -2 : -1);
+            const float* prow = plane + (y_min + r) * w + x_min;
+            const float s0 = prow[clampi(sx, 0, pw - 1)], s1 = prow[clampi(sx + 1, 0, pw - 1)];
+            const float s2 = prow[clampi(sx + 2, 0, pw - 1)], s3 = prow[clampi(sx + 3, 0, pw - 1)];
+            float v = __fmul_rn(s0, c_cubic[phase][0]);
+            v = __fadd_rn(v, __fmul_rn(s1, c_cubic[phase][1]));
+            v = __fadd_rn(v, __fmul_rn(s2, c_cubic[phase][2]));
+            v = __fadd_rn(v, __fmul_rn(s3, c_cubic[phase][3]));
+            hor[r * kHorStride + X] = v;
+        }
+        __syncwarp();
+        float best = -INFINITY;
+        int best_idx = 0x7fffffff;
+        for (int idx = lane; idx < H8 * W8; idx += 32) {
+            const int Y = idx / W8, X = idx - Y * W8;
+            const int phase = Y & 7;
+            const int sy = (Y >> 3) + (phase < 4 ? -2 : -1);
+            const float S0 = hor[clampi(sy, 0, ph - 1) * kHorStride + X];
+            const float S1 = hor[clampi(sy + 1, 0, ph - 1) * kHorStride + X];
+            const float S2 = hor[clampi(sy + 2, 0, ph - 1) * kHorStride + X];
+            const float S3 = hor[clampi(sy + 3, 0, ph - 1) * kHorStride + X];
+            float v = __fmul_rn(S3, c_cubic[phase][3]);
+            v = __fadd_rn(__fmul_rn(S2, c_cubic[phase][2]), v);
+            v = __fadd_rn(__fmul_rn(S1, c_cubic[phase][1]), v);
+            v = __fadd_rn(__fmul_rn(S0, c_cubic[phase][0]), v);
+            if (v > best) { best = v; best_idx = idx; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+            if (ov > best || (ov == best && oi < best_idx)) { best = ov; best_idx = oi; }
+        }
+        if (lane == 0) {
+            const int ay = best_idx / W8, ax = best_idx - ay * W8;
+            px[pk] = 8 * x_min + ax;     // == (x+0.5)*8-0.5 + (ax - ((x-x_min+0.5)*8-0.5)), paf_to_pose.py:126-139
+            py[pk] = 8 * y_min + ay;
+            ps[pk] = best;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ limbs
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scratch /*[threads/32 + 1]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        int w = lane < nw ? scratch[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < nw) scratch[lane] = winc - w;
+        if (lane == nw - 1) scratch[nw] = winc;
+    }
+    __syncthreads();
+    const int res = scratch[warp] + inc - v;
+    *total = scratch[blockDim.x >> 5];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up) {
+    extern __shared__ unsigned long long sm_keys[];       // [cand_smem_cap]
+    __shared__ uint32_t used_a[64], used_b[64];            // peak_cap <= 2048
+    __shared__ int scan_scratch[kLimbThreads / 32 + 1];
+    __shared__ long s_pool_base;
+    const int limb = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    const int pa = c_limb_parts[limb][0], pbp = c_limb_parts[limb][1];
+    const int c1 = c_limb_paf[limb][0], c2 = c_limb_paf[limb][1];
+    const int cap = pb.peak_cap;
+    const int na = pb.counts[img * kNumPart + pa], nb = pb.counts[img * kNumPart + pbp];
+    int* out_cnt = pb.conn_cnt + img * kNumLimb + limb;
+    if (na == 0 || nb == 0) {
+        if (tid == 0) *out_cnt = 0;
+        return;
+    }
+    const int* ax = pb.peak_x + ((long)img * kNumPart + pa) * cap;
+    const int* ay = pb.peak_y + ((long)img * kNumPart + pa) * cap;
+    const int* bx = pb.peak_x + ((long)img * kNumPart + pbp) * cap;
+    const int* by = pb.peak_y + ((long)img * kNumPart + pbp) * cap;
+    PafView paf = paf0;
+    paf.base += img * p_img;
+
+    const int npairs = na * nb;
+    const int per = (npairs + kLimbThreads - 1) / kLimbThreads;
+    const int p_begin = min(npairs, tid * per), p_end = min(npairs, p_begin + per);
+
+    int cnt = 0;
+    for (int p = p_begin; p < p_end; ++p) {
+        const int a = p / nb, b = p - a * nb;
+        float s;
+        if (pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &s)) ++cnt;
+    }
+    int n;
+    const int off0 = block_exclusive_scan(cnt, &n, scan_scratch);
+    if (n == 0) {
+        if (tid == 0) *out_cnt = 0;
+        return;
+    }
+    int npow2 = 1;
+    while (npow2 < n) npow2 <<= 1;
+    unsigned long long* keys = sm_keys;
+    if (npow2 > pb.cand_smem_cap) {
+        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, (unsigned long long)npow2);
+        __syncthreads();
+        if (s_pool_base + npow2 > pb.pool_cap) {
+            if (tid == 0) {
+                atomicOr(&pb.status[img], 2);
+                *out_cnt = 0;
+            }
+            return;
+        }
+        keys = pb.pool + s_pool_base;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: keys in generation order -> parallel sort; pass 1 (only if equal scores exist): regenerate in
+        // generation order and reproduce std::sort's permutation sequentially.
+        int off = off0;
+        for (int p = p_begin; p < p_end; ++p) {
+            const int a = p / nb, b = p - a * nb;
+            float s;
+            if (pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &s)) keys[off++] = cand_key(s, (uint32_t)p);
+        }
+        if (pass == 1) {
+            __syncthreads();
+            if (tid == 0) {
+                seq_std_sort(reinterpret_cast<uint64_t*>(keys), n);
+                atomicAdd(&pb.status[img], 256);
+            }
+            __syncthreads();
+            break;
+        }
+        for (int i = n + tid; i < npow2; i += kLimbThreads) keys[i] = ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= npow2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < npow2; i += kLimbThreads) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long x = keys[i], y = keys[ixj];
+                        const bool asc = (i & k) == 0;
+                        if ((x > y) == asc) { keys[i] = y; keys[ixj] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        int tie = 0;
+        for (int i = tid; i + 1 < n; i += kLimbThreads) tie |= ((keys[i] >> 32) == (keys[i + 1] >> 32));
+        if (!__syncthreads_or(tie)) break;
+    }
+    for (int i = tid; i < 64; i += kLimbThreads) { used_a[i] = 0; used_b[i] = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        const long o = ((long)img * kNumLimb + limb) * cap;
+        *out_cnt = greedy_match(reinterpret_cast<const uint64_t*>(keys), n, nb, used_a, used_b, min(na, nb),
+                                pb.conn_a + o, pb.conn_b + o, pb.conn_s + o);
+    }
+}
+
+// ------------------------------------------------------------------ assembly
+__global__ void __launch_bounds__(kAsmThreads) assemble_kernel(PostBuffers pb) {
+    extern __shared__ int sm_kept[];     // [human_cap]
+    __shared__ int part_base[kNumPart + 1];
+    __shared__ int s_nh, s_nrows;
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int cap = pb.peak_cap;
+    const int id_cap = kNumPart * cap;
+    if (tid == 0) {
+        part_base[0] = 0;
+        for (int p = 0; p < kNumPart; ++p) part_base[p + 1] = part_base[p] + pb.counts[img * kNumPart + p];
+    }
+    __syncthreads();
+    float* id_score = pb.id_score + (long)img * id_cap;
+    int* id_xy = pb.id_xy + (long)img * id_cap * 2;
+    uint8_t* list_n = pb.list_n + (long)img * id_cap;
+    uint8_t* alive = pb.alive + (long)img * pb.row_cap;
+    const int total = part_base[kNumPart];
+    for (int p = 0; p < kNumPart; ++p) {
+        const int n = part_base[p + 1] - part_base[p];
+        const long src = ((long)img * kNumPart + p) * cap;
+        for (int i = tid; i < n; i += kAsmThreads) {
+            const int id = part_base[p] + i;
+            id_score[id] = pb.peak_s[src + i];
+            id_xy[2 * id] = pb.peak_x[src + i];
+            id_xy[2 * id + 1] = pb.peak_y[src + i];
+        }
+    }
+    for (int i = tid; i < total; i += kAsmThreads) list_n[i] = 0;
+    for (int i = tid; i < pb.row_cap; i += kAsmThreads) alive[i] = 0;
+    __syncthreads();
+
+    float* rows = pb.rows + (long)img * pb.row_cap * kRowFloats;
+    if (tid == 0) {
+        Assembler as;
+        as.rows = rows;
+        as.alive = alive;
+        as.lists = pb.lists + (long)img * id_cap * kListCap;
+        as.list_n = list_n;
+        as.part_base = part_base;
+        as.peak_score = id_score;
+        as.row_cap = pb.row_cap;
+        as.nrows = 0;
+        as.degraded = 0;
+        as.overflow = 0;
+        for (int l = 0; l < kNumLimb; ++l) {
+            const int p1 = c_limb_parts[l][0], p2 = c_limb_parts[l][1];
+            const int nc = pb.conn_cnt[img * kNumLimb + l];
+            const long o = ((long)img * kNumLimb + l) * cap;
+            for (int c = 0; c < nc; ++c)
+                as.add_connection(l, p1, p2, part_base[p1] + pb.conn_a[o + c], part_base[p2] + pb.conn_b[o + c],
+                                  pb.conn_s[o + c]);
+        }
+        int nh = 0, st = 0;
+        for (int r = 0; r < as.nrows; ++r)
+            if (as.keep(r)) {
+                if (nh < pb.human_cap) sm_kept[nh++] = r;
+                else st |= 8;
+            }
+        if (as.overflow) st |= 4;
+        if (as.degraded) st |= 16;
+        if (st) atomicOr(&pb.status[img], st);
+        s_nh = nh;
+        s_nrows = as.nrows;
+        pb.n_humans[img] = nh;
+    }
+    __syncthreads();
+    const int nh = s_nh;
+    float* out = pb.humans + (long)img * pb.human_cap * kHumanFloats;
+    for (int e = tid; e < nh * kHumanFloats; e += kAsmThreads) {
+        const int hi = e / kHumanFloats, f = e - hi * kHumanFloats;
+        const float* row = rows + sm_kept[hi] * kRowFloats;
+        float v;
+        if (f == 0) v = __fdiv_rn(row[18], row[19]);     // get_score, pafprocess.cpp:204-206
+        else {
+            const int p = (f - 1) >> 2, k = (f - 1) & 3;
+            const int cid = (int)row[p];                  // get_part_cid truncation, pafprocess.cpp:200-202
+            if (cid < 0) v = (k == 3) ? -1.f : 0.f;
+            else v = k == 0 ? (float)id_xy[2 * cid] : k == 1 ? (float)id_xy[2 * cid + 1] : k == 2 ? id_score[cid] : (float)cid;
+        }
+        out[e] = v;
+    }
+}
+
+}  // namespace
+
+#define B2P_TRY(x)                        \
+    do {                                  \
+        cudaError_t e_ = (x);             \
+        if (e_ != cudaSuccess) return e_; \
+    } while (0)
+
+cudaError_t post_alloc(PostBuffers& pb, int batch_cap, int peak_cap, int human_cap, long pool_cap) {
+    memset(&pb, 0, sizeof(pb));
+    if (peak_cap > 2048 || peak_cap < 1) return cudaErrorInvalidValue;
+    pb.batch_cap = batch_cap;
+    pb.peak_cap = peak_cap;
+    pb.human_cap = human_cap;
+    pb.cand_smem_cap = 4096;
+    pb.pool_cap = pool_cap;
+    pb.row_cap = 4 * peak_cap;
+    const long B = batch_cap;
+    B2P_TRY(cudaMalloc(&pb.counts, B * kNumPart * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.peak_x, B * kNumPart * peak_cap * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.peak_y, B * kNumPart * peak_cap * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.peak_s, B * kNumPart * peak_cap * sizeof(float)));
+    B2P_TRY(cudaMalloc(&pb.conn_cnt, B * kNumLimb * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.conn_a, B * kNumLimb * peak_cap * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.conn_b, B * kNumLimb * peak_cap * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.conn_s, B * kNumLimb * peak_cap * sizeof(float)));
+    B2P_TRY(cudaMalloc(&pb.rows, B * pb.row_cap * kRowFloats * sizeof(float)));
+    B2P_TRY(cudaMalloc(&pb.alive, B * pb.row_cap));
+    B2P_TRY(cudaMalloc(&pb.lists, B * kNumPart * peak_cap * kListCap * sizeof(int32_t)));
+    B2P_TRY(cudaMalloc(&pb.list_n, B * kNumPart * peak_cap));
+    B2P_TRY(cudaMalloc(&pb.id_score, B * kNumPart * peak_cap * sizeof(float)));
+    B2P_TRY(cudaMalloc(&pb.id_xy, B * kNumPart * peak_cap * 2 * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.pool, pool_cap * sizeof(unsigned long long)));
+    B2P_TRY(cudaMalloc(&pb.pool_cursor, sizeof(unsigned long long)));
+    B2P_TRY(cudaMalloc(&pb.n_humans, B * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.humans, B * human_cap * kHumanFloats * sizeof(float)));
+    B2P_TRY(cudaMalloc(&pb.status, B * sizeof(int)));
+    B2P_TRY(cudaMemset(pb.status, 0, B * sizeof(int)));
+    B2P_TRY(cudaMemset(pb.counts, 0, B * kNumPart * sizeof(int)));
+    return cudaSuccess;
+}
+
+void post_free(PostBuffers& pb) {
+    void* ptrs[] = {pb.counts, pb.peak_x, pb.peak_y, pb.peak_s,  pb.conn_cnt, pb.conn_a,      pb.conn_b,
+                    pb.conn_s, pb.rows,   pb.alive,  pb.lists,   pb.list_n,   pb.id_score,    pb.id_xy,
+                    pb.pool,   pb.pool_cursor, pb.n_humans, pb.humans, pb.status};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    memset(&pb, 0, sizeof(pb));
+}
+
+cudaError_t post_peaks(const PostBuffers& pb, int batch, const float* heat, long h_img, long h_ch, long h_y, long h_x,
+                       int h, int w, float thresh, cudaStream_t s) {
+    if (batch > pb.batch_cap) return cudaErrorInvalidValue;
+    const size_t smem = ((size_t)h * w + (kPeakThreads / 32) * 5 * kHorStride) * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        B2P_TRY(cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    B2P_TRY(cudaMemsetAsync(pb.status, 0, batch * sizeof(int), s));
+    peaks_kernel<<<dim3(kNumPart, batch), kPeakThreads, smem, s>>>(pb, heat, h_img, h_ch, h_y, h_x, h, w, thresh);
+    return cudaGetLastError();
+}
+
+cudaError_t post_limbs_and_assemble(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
+                                    long p_x, int shift, int h_up, cudaStream_t s) {
+    if (batch > pb.batch_cap) return cudaErrorInvalidValue;
+    B2P_TRY(cudaMemsetAsync(pb.pool_cursor, 0, sizeof(unsigned long long), s));
+    PafView pv{paf, p_ch, p_y, p_x, shift};
+    limbs_kernel<<<dim3(kNumLimb, batch), kLimbThreads, pb.cand_smem_cap * sizeof(unsigned long long), s>>>(pb, pv, p_img,
+                                                                                                           h_up);
+    B2P_TRY(cudaGetLastError());
+    assemble_kernel<<<batch, kAsmThreads, pb.human_cap * sizeof(int), s>>>(pb);
+    return cudaGetLastError();
+}
+
+}  // namespace b2p

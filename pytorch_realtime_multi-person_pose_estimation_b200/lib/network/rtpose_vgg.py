@@ -1,0 +1,112 @@
+"""Drop-in for /root/reference/lib/network/rtpose_vgg.py on the inference path.
+
+`get_model('vgg19')` returns an nn.Module whose state_dict has the reference's 184 keys/shapes
+(model0.{0,2,5,...}, model{1..6}_{1,2}.{0,2,...}; rtpose_vgg.py:69-127, 140-156), so
+`model.load_state_dict(torch.load(w))`, `.cuda()`, `.float()`, `.eval()` and `torch.nn.DataParallel(model)`
+(demo/picture_demo.py:45-49) work unchanged.  `forward` (rtpose_vgg.py:158-198) does NOT run nn.Conv2d: it hands
+the input's device pointer to libb200pose.so, which runs the hand-written sm_100a kernels, and returns
+`((paf, heat), saved_for_loss[12])` as CUDA fp32 NCHW tensors.
+
+Precision: `model.precision = 'bf16'` (default; tcgen05 tensor cores, fp32 accumulate) or `'fp32'` (parity mode);
+the environment variable B200POSE_MODE sets the default.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from ... import _native as nat
+from ...engine import NativeNet
+
+_TRUNK = [(3, 64), (64, 64), "P", (64, 128), (128, 128), "P", (128, 256), (256, 256), (256, 256), (256, 256), "P",
+          (256, 512), (512, 512), (512, 256), (256, 128)]
+
+
+def _stage_spec(stage, out_ch):
+    if stage == 1:
+        return [(128, 128, 3)] * 3 + [(128, 512, 1), (512, out_ch, 1)]
+    return [(185, 128, 7)] + [(128, 128, 7)] * 4 + [(128, 128, 1), (128, out_ch, 1)]
+
+
+def _make_trunk():
+    layers = []
+    for item in _TRUNK:
+        if item == "P":
+            layers.append(nn.MaxPool2d(2, 2, 0))
+        else:
+            layers += [nn.Conv2d(item[0], item[1], 3, 1, 1), nn.ReLU(inplace=True)]
+    return nn.Sequential(*layers)
+
+
+def _make_branch(spec):
+    layers = []
+    for i, (cin, cout, k) in enumerate(spec):
+        layers.append(nn.Conv2d(cin, cout, k, 1, k // 2))
+        if i != len(spec) - 1:          # the last conv of a branch has no ReLU (rtpose_vgg.py:30-35)
+            layers.append(nn.ReLU(inplace=True))
+    return nn.Sequential(*layers)
+
+
+class rtpose_model(nn.Module):
+    """Parameter container with the reference layout + native forward."""
+
+    def __init__(self):
+        super().__init__()
+        self.model0 = _make_trunk()
+        for s in range(1, 7):
+            setattr(self, "model%d_1" % s, _make_branch(_stage_spec(s, 38)))
+        for s in range(1, 7):
+            setattr(self, "model%d_2" % s, _make_branch(_stage_spec(s, 19)))
+        self.precision = os.environ.get("B200POSE_MODE", "bf16")
+        self._engines = {}     # device index -> (signature, NativeNet); shared by DataParallel replicas
+        for m in self.modules():   # same init as rtpose_vgg.py:200-222
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, std=0.01)
+                nn.init.constant_(m.bias, 0.0)
+
+    def _signature(self):
+        ps = list(self.parameters())
+        return tuple((p.data_ptr(), p._version) for p in (ps[0], ps[len(ps) // 2], ps[-1]))
+
+    def _engine(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        sig = self._signature()
+        cached = self._engines.get(idx)
+        if cached is None or cached[0] != sig:
+            net = cached[1] if cached is not None else NativeNet(idx)
+            arrays = [p.detach().to(torch.float32).cpu().contiguous().numpy() for p in self.state_dict().values()]
+            net.load_state_dict_arrays(arrays)
+            self._engines[idx] = (sig, net)
+        return self._engines[idx][1]
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise nat.B200PoseError("rtpose_model.forward needs a CUDA tensor: this build has no CPU fallback")
+        if self.precision not in nat.MODES:
+            raise ValueError("precision must be one of %s" % list(nat.MODES))
+        x = x.contiguous().to(torch.float32)
+        n, c, H, W = x.shape
+        if c != 3 or H % 8 or W % 8:
+            raise ValueError("expected [N,3,H,W] with H, W multiples of 8, got %s" % (tuple(x.shape),))
+        net = self._engine(x.device)
+        h, w = H // 8, W // 8
+        saved = [torch.empty((n, 38 if i % 2 == 0 else 19, h, w), dtype=torch.float32, device=x.device)
+                 for i in range(12)]
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            net.forward_ptr(x.data_ptr(), True, n, H, W, nat.MODES[self.precision], [t.data_ptr() for t in saved], True,
+                            stream)
+        return (saved[-2], saved[-1]), saved
+
+
+def get_model(trunk='vgg19'):
+    """rtpose_vgg.py:60.  Only the VGG19 trunk exists on this path (BASELINE.json north_star)."""
+    if trunk != 'vgg19':
+        raise NotImplementedError("only trunk='vgg19' is built for the B200 path")
+    return rtpose_model()
+
+
+def use_vgg(model):
+    """rtpose_vgg.py:235-251 downloads ImageNet VGG19 weights; there is no network here."""
+    raise RuntimeError("use_vgg() needs network access (torchvision VGG19 weights); load a checkpoint instead")

@@ -1,0 +1,219 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI / the reference-shaped Python surface, against
+the oracle (CPU) on seeded inputs and against the committed golden vectors of the reference."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import POST_CASES, ROOT, assert_humans_equal, golden, humans_rows_to_dicts, pkg_module
+from oracle import glue_port, net_port, nms_port, pafprocess_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3          # BASELINE.json north_star: heat/PAF within 1e-3 max-abs in fp32
+BF16_TOL = 0.15          # bf16 operands through 52 conv layers, outputs O(1..4); measured value is printed
+
+
+@pytest.fixture(scope="module")
+def native_net(built, he_sd):
+    eng = pkg_module("engine")
+    net = eng.NativeNet(0)
+    net.load_state_dict_arrays([v.numpy() for v in he_sd.values()])
+    return net
+
+
+def _forward(net, x, mode):
+    nat = pkg_module("_native")
+    n, _, H, W = x.shape
+    outs = [torch.empty((n, 38 if i % 2 == 0 else 19, H // 8, W // 8), device="cuda") for i in range(12)]
+    xd = x.cuda().contiguous()
+    net.forward_ptr(xd.data_ptr(), True, n, H, W, nat.MODES[mode], [o.data_ptr() for o in outs], True,
+                    torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return [o.cpu() for o in outs]
+
+
+def test_tcgen05_conv_kernel_cases(built):
+    """Standalone harness: 7 conv configurations (1x1/3x3/7x7, groups, fused pool, padded heads, 4 n-tiles) against
+    a plain CPU loop."""
+    r = subprocess.run([os.path.join(ROOT, "build", "test_conv_tc")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0 and "ALL OK" in r.stdout
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_net_all_stages_vs_oracle_small(native_net, he_sd, mode, tol):
+    x = torch.rand((2, 3, 64, 72), generator=torch.Generator().manual_seed(5)) - 0.5
+    with torch.no_grad():
+        _, saved = net_port.forward(he_sd, x)
+    outs = _forward(native_net, x, mode)
+    errs = [float((o - s).abs().max()) for o, s in zip(outs, saved)]
+    print("mode %s per-stage max|err|: %s" % (mode, " ".join("%.2e" % e for e in errs)))
+    assert max(errs) < tol
+    assert float(saved[-1].abs().max()) > 0.3
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_net_368_vs_reference_golden(native_net, mode, tol):
+    g = golden("net_368")
+    x = torch.rand((1, 3, 368, 368), generator=torch.Generator().manual_seed(int(g["seed"]))) - 0.5
+    outs = _forward(native_net, x, mode)
+    e_paf = float(np.abs(outs[10].numpy() - g["paf"]).max())
+    e_heat = float(np.abs(outs[11].numpy() - g["heat"]).max())
+    print("368x368 %s: max|paf err| %.3e max|heat err| %.3e (|paf|max %.2f)" % (mode, e_paf, e_heat, np.abs(g["paf"]).max()))
+    assert e_paf < tol and e_heat < tol
+    np.testing.assert_allclose([float(o.abs().max()) for o in outs], g["stage_absmax"], rtol=0.05 if mode == "bf16" else 1e-3)
+
+
+def test_batch_rows_are_independent_and_deterministic(native_net):
+    """Size-independent property at the full bench shape: image i of a batch of 32 equals image i run alone (bit for
+    bit), and two runs are identical."""
+    x = torch.rand((32, 3, 368, 368), generator=torch.Generator().manual_seed(9)) - 0.5
+    a = _forward(native_net, x, "bf16")
+    b = _forward(native_net, x, "bf16")
+    for i in (10, 11):
+        assert torch.equal(a[i], b[i])
+    for idx in (0, 17, 31):
+        single = _forward(native_net, x[idx:idx + 1], "bf16")
+        assert torch.equal(single[10][0], a[10][idx]) and torch.equal(single[11][0], a[11][idx])
+
+
+def test_module_surface_matches_native(built, he_sd):
+    import lib.network.rtpose_vgg as m
+    model = m.get_model("vgg19")
+    model.load_state_dict(he_sd)
+    model = torch.nn.DataParallel(model).cuda()      # demo/picture_demo.py:47
+    model.float()
+    model.eval()
+    x = torch.rand((1, 3, 64, 64), generator=torch.Generator().manual_seed(3)) - 0.5
+    model.module.precision = "fp32"
+    with torch.no_grad():
+        (paf, heat), saved = model(x.cuda())
+        (paf_o, heat_o), saved_o = net_port.forward(he_sd, x)
+    assert len(saved) == 12 and paf.shape == (1, 38, 8, 8) and heat.shape == (1, 19, 8, 8) and paf.is_cuda
+    assert float((paf.cpu() - paf_o).abs().max()) < FP32_TOL and float((heat.cpu() - heat_o).abs().max()) < FP32_TOL
+    for s, so in zip(saved, saved_o):
+        assert float((s.cpu() - so).abs().max()) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", sorted(POST_CASES))
+def test_post_kernels_vs_oracle_and_reference_golden(name, built):
+    eng = pkg_module("engine")
+    heat, paf = POST_CASES[name](synth)
+    h, w = heat.shape[:2]
+    post = eng.NativePost(0, batch_cap=1, peak_cap=1024, human_cap=1024)
+    post.run(heat.ctypes.data, paf.ctypes.data, False, 1, 1, h, w, 0.1)
+    post.sync()
+    post.check_status(1)
+    # peaks: identical to the oracle NMS (coordinates, ids, parts AND scores: same float ops in the same order)
+    jl = nms_port.joint_list_from_nms(nms_port.nms(heat, 0.1))
+    got_jl = post.peaks(0)
+    assert got_jl.shape == jl.shape
+    np.testing.assert_array_equal(got_jl, jl)
+    # humans: identical to the oracle port and to the reference's golden output
+    _, want = glue_port.paf_to_pose(heat, paf, pafprocess_oracle.load_port())
+    got = eng.humans_to_dicts(post.humans(0), w * 8, h * 8)
+    assert_humans_equal(got, want, score_tol=0.0)
+    assert_humans_equal(got, humans_rows_to_dicts(golden("post_" + name)["humans"]), score_tol=1e-6)
+    print(name, "peaks", len(jl), "humans", len(got), "status", post.status(0))
+
+
+def test_post_batch_and_nchw_layout(built):
+    eng = pkg_module("engine")
+    maps = [synth.stick_figures(p, s)[:2] for p, s in ((2, 21), (6, 22), (12, 23), (1, 24))]
+    heat = np.stack([m[0] for m in maps]).transpose(0, 3, 1, 2).copy()      # NCHW
+    paf = np.stack([m[1] for m in maps]).transpose(0, 3, 1, 2).copy()
+    post = eng.NativePost(0, batch_cap=4, peak_cap=256, human_cap=128)
+    post.run(heat.ctypes.data, paf.ctypes.data, False, 0, 4, 46, 46, 0.1)
+    post.sync()
+    post.check_status(4)
+    port = pafprocess_oracle.load_port()
+    for i, (hm, pf) in enumerate(maps):
+        _, want = glue_port.paf_to_pose(hm, pf, port)
+        assert_humans_equal(eng.humans_to_dicts(post.humans(i), 368, 368), want, score_tol=0.0)
+
+
+def test_capacity_overflow_is_loud(built):
+    eng, nat = pkg_module("engine"), pkg_module("_native")
+    heat, paf = synth.noise_maps(1)
+    post = eng.NativePost(0, batch_cap=1, peak_cap=64, human_cap=16)
+    post.run(heat.ctypes.data, paf.ctypes.data, False, 1, 1, 46, 46, 0.1)
+    post.sync()
+    with pytest.raises(nat.B200PoseError):
+        post.check_status(1)
+
+
+def test_legacy_pafprocess_surface(built):
+    """lib.pafprocess.pafprocess called exactly like the SWIG module (upsampled maps, getters)."""
+    from lib.pafprocess import pafprocess
+    port = pafprocess_oracle.load_port()
+    for persons, seed in ((3, 3), (8, 8), (30, 30)):
+        heat, paf, _ = synth.stick_figures(persons, seed)
+        jl = nms_port.joint_list_from_nms(nms_port.nms(heat, 0.1))
+        paf_up = np.ascontiguousarray(np.repeat(np.repeat(paf, 8, 0), 8, 1))
+        heat_up = np.ascontiguousarray(np.repeat(np.repeat(heat, 8, 0), 8, 1))
+        assert pafprocess.process_paf(jl[None], heat_up, paf_up) == 0
+        port.process_paf(jl[None], heat_up, paf_up)
+        assert pafprocess.get_num_humans() == port.get_num_humans() > 0
+        for hid in range(port.get_num_humans()):
+            assert pafprocess.get_score(hid) == port.get_score(hid)
+            for p in range(18):
+                c = pafprocess.get_part_cid(hid, p)
+                assert c == port.get_part_cid(hid, p)
+                if c >= 0:
+                    assert (pafprocess.get_part_x(c), pafprocess.get_part_y(c), pafprocess.get_part_score(c)) == \
+                           (port.get_part_x(c), port.get_part_y(c), port.get_part_score(c))
+    with pytest.raises(TypeError):
+        pafprocess.process_paf(jl[None].astype(np.float64), heat_up, paf_up)
+
+
+def test_reference_shaped_pipeline_end_to_end(built, he_sd):
+    """get_outputs + paf_to_pose_cpp (the calls demo/picture_demo.py makes) vs the oracle glue, fp32 mode."""
+    from evaluate.coco_eval import get_outputs
+    from lib.config import cfg
+    from lib.network.rtpose_vgg import get_model
+    from lib.utils.paf_to_pose import NMS, paf_to_pose_cpp
+    model = get_model("vgg19")
+    model.load_state_dict(he_sd)
+    model = model.cuda().float().eval()
+    model.precision = "fp32"
+    g = golden("get_outputs_200x230")
+    img = np.random.RandomState(0).randint(0, 256, (200, 230, 3)).astype(np.uint8)
+    with torch.no_grad():
+        paf, heat, scale = get_outputs(img, model, "rtpose")
+    assert paf.shape == (46, 53, 38) and heat.shape == (46, 53, 19) and abs(scale - float(g["scale"])) < 1e-12
+    assert np.abs(paf - g["paf"]).max() < FP32_TOL and np.abs(heat - g["heat"]).max() < FP32_TOL
+    # post-processing on the REFERENCE's maps so that the comparison is exact
+    humans = paf_to_pose_cpp(g["heat"], g["paf"], cfg)
+    _, want = glue_port.paf_to_pose(g["heat"], g["paf"], pafprocess_oracle.load_port())
+    got = [(h.score, {p: (b.x, b.y, b.score) for p, b in h.body_parts.items()}) for h in humans]
+    assert_humans_equal(got, want, score_tol=0.0)
+    per_joint = NMS(g["heat"], upsampFactor=8, config=cfg)
+    ref_pj = nms_port.nms(g["heat"], 0.1)
+    for a, b in zip(per_joint, ref_pj):
+        np.testing.assert_array_equal(a, b.astype(np.float32).astype(np.float64))
+    assert paf_to_pose_cpp(np.zeros((46, 46, 19), np.float32), np.zeros((46, 46, 38), np.float32), cfg) == []
+
+
+def test_fused_engine_matches_stagewise(built, he_sd):
+    """b200pose_infer (maps never leave the device) == forward + separate post on the same maps."""
+    eng = pkg_module("engine")
+    pe = eng.PoseEngine([v.numpy() for v in he_sd.values()], 0, mode="bf16", batch_cap=4, peak_cap=1024, human_cap=1024)
+    x = (np.random.RandomState(3).rand(4, 3, 368, 368).astype(np.float32) - 0.5)
+    fused = pe.infer_batch(x)
+    outs = [torch.empty((4, 38 if i % 2 == 0 else 19, 46, 46), device="cuda") for i in range(12)]
+    xd = torch.from_numpy(x).cuda()
+    pe.net.forward_ptr(xd.data_ptr(), True, 4, 368, 368, pe.mode, [o.data_ptr() for o in outs], True,
+                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    port = pafprocess_oracle.load_port()
+    for i in range(4):
+        heat = outs[11][i].permute(1, 2, 0).contiguous().cpu().numpy()
+        paf = outs[10][i].permute(1, 2, 0).contiguous().cpu().numpy()
+        _, want = glue_port.paf_to_pose(heat, paf, port)
+        assert_humans_equal(fused[i], want, score_tol=0.0)
+    assert pkg_module("_native").launch_count() > 0

@@ -1,0 +1,158 @@
+"""CPU: host-side logic, the C-ABI surface, and the sequential-exact device cores compiled for the host."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import POST_CASES, ROOT, assert_humans_equal, pkg_module
+from oracle import glue_port, net_port, nms_port, pafprocess_oracle, synth
+
+
+def test_library_exports_every_declared_symbol(built):
+    header = open(os.path.join(ROOT, "include", "b200pose.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", header)) - {"defined", "void"}
+    nat = pkg_module("_native")
+    assert os.path.exists(nat.LIB_PATH)
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, "declared in include/b200pose.h but not exported: %s" % missing
+    assert set(nat.EXPORTED) <= declared
+    assert lib.b200pose_version() == 100
+    dims = (ctypes.c_long * 4)()
+    assert lib.b200pose_net_tensor_shape(0, dims) == 4 and list(dims) == [64, 3, 3, 3]
+    assert lib.b200pose_net_tensor_shape(183, dims) == 1 and dims[0] == 19
+
+
+def test_no_cpu_fallback(built):
+    nat = pkg_module("_native")
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    h = ctypes.c_void_p()
+    assert nat.lib().b200pose_net_create(ctypes.byref(h), 0) != 0
+    assert b"no CUDA device" in nat.lib().b200pose_last_error()
+    model = pkg_module("lib.network.rtpose_vgg").get_model("vgg19")
+    with pytest.raises(nat.B200PoseError):
+        model(torch.zeros(1, 3, 16, 16))
+
+
+def test_product_never_touches_the_oracle():
+    """The product path must not import / link / execute anything under oracle/ (nor read /root/reference)."""
+    pkg = os.path.join(ROOT, "pytorch_realtime_multi-person_pose_estimation_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|libpafprocess_(port|ref)|oracle[/.](net_port|nms_port|glue_port|synth)"
+                     r"|open\(.*/root/reference|sys\.path.*reference", re.M)
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) and pat.search(open(os.path.join(d, f), errors="ignore").read()):
+                offenders.append(os.path.join(d, f))
+    for f in ("lib/__init__.py", "evaluate/__init__.py", "_b200_alias.py"):
+        if pat.search(open(os.path.join(ROOT, f)).read()):
+            offenders.append(f)
+    assert not offenders, offenders
+
+
+def test_model_has_reference_state_dict_and_loads_strictly(he_sd):
+    import lib.network.rtpose_vgg as m        # the reference's import path, aliased to the package
+    model = m.get_model("vgg19")
+    sd = model.state_dict()
+    spec = net_port.state_dict_spec()
+    assert list(sd) == list(spec) and all(tuple(sd[k].shape) == spec[k] for k in spec)
+    model.load_state_dict(he_sd, strict=True)
+    prefixed = {"model." + k: v for k, v in he_sd.items()}       # evaluation.py:13-23 strips a 6-char prefix
+    model.load_state_dict({k[6:]: v for k, v in prefixed.items()}, strict=True)
+    assert model.float().eval() is model
+    with pytest.raises(NotImplementedError):
+        m.get_model("mobilenet")
+
+
+def test_reference_import_paths_resolve():
+    from evaluate.coco_eval import get_outputs, handle_paf_and_heat          # noqa: F401
+    from lib.config import cfg, update_config
+    from lib.network import im_transform
+    from lib.pafprocess import pafprocess
+    from lib.utils.common import BodyPart, CocoColors, CocoPairsRender, CocoPart, Human, draw_humans  # noqa: F401
+    from lib.utils.paf_to_pose import paf_to_pose_cpp                          # noqa: F401
+    assert cfg.DATASET.IMAGE_SIZE == 368 and cfg.MODEL.DOWNSAMPLE == 8 and cfg.TEST.THRESH_HEATMAP == 0.1
+    class A: cfg = os.path.join(ROOT, "experiments", "vgg19_368x368_sgd.yaml"); opts = ["TEST.THRESH_HEATMAP", "0.2"]
+    update_config(cfg, A)
+    assert cfg.TEST.THRESH_HEATMAP == 0.2 and cfg.MODEL.NUM_KEYPOINTS == 18
+    cfg.defrost(); cfg.TEST.THRESH_HEATMAP = 0.1; cfg.freeze()
+    assert all(hasattr(pafprocess, n) for n in ("process_paf", "get_num_humans", "get_part_cid", "get_score",
+                                                 "get_part_x", "get_part_y", "get_part_score"))
+    assert len(CocoPairsRender) == 17 and CocoPart.Background.value == 18
+    img = np.random.RandomState(0).randint(0, 256, (200, 230, 3)).astype(np.uint8)
+    a, s, shp = im_transform.crop_with_factor(img, 368, factor=8, is_ceil=True)
+    b, s2, shp2 = glue_port.crop_with_factor(img, 368, 8)
+    assert a.shape == (368, 424, 3) and s == s2 and shp == shp2
+    np.testing.assert_array_equal(a, b)
+
+
+def test_preprocess_and_flip_match_oracle():
+    pre = pkg_module("lib.datasets.preprocessing")
+    ev = pkg_module("evaluate.coco_eval")
+    img = np.random.RandomState(5).randint(0, 256, (16, 24, 3)).astype(np.uint8)
+    np.testing.assert_array_equal(pre.rtpose_preprocess(img), glue_port.rtpose_preprocess(img))
+    np.testing.assert_allclose(pre.vgg_preprocess(img), glue_port.vgg_preprocess(img), atol=1e-6)
+    rs = np.random.RandomState(6)
+    nh, fh, npf, fpf = (rs.rand(6, 5, c).astype(np.float32) for c in (19, 19, 38, 38))
+    ap, ah = ev.handle_paf_and_heat(nh.copy(), fh.copy(), npf.copy(), fpf.copy())
+    bp, bh = glue_port.handle_paf_and_heat(nh, fh, npf, fpf)
+    np.testing.assert_array_equal(ap, bp)
+    np.testing.assert_array_equal(ah, bh)
+
+
+@pytest.mark.parametrize("name", sorted(POST_CASES))
+def test_device_cores_on_host_match_oracle(name, built):
+    """csrc/post_core.h (pair scoring, std::sort emulation, greedy matching, indexed person assembly) compiled
+    for the host must reproduce the oracle exactly - same code the CUDA kernels execute."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "build", "libpostcore_host.so"))
+    FP = ctypes.POINTER(ctypes.c_float)
+    lib.core_process.argtypes = [ctypes.c_int, FP, ctypes.c_int, FP, ctypes.c_long, ctypes.c_long, ctypes.c_long,
+                                 ctypes.c_int, ctypes.c_int]
+    lib.core_result.restype = FP
+    heat, paf = POST_CASES[name](synth)
+    h, w = heat.shape[:2]
+    jl, want = glue_port.paf_to_pose(heat, paf, pafprocess_oracle.load_port())
+    jl = np.ascontiguousarray(jl)
+    paf = np.ascontiguousarray(paf)
+    nh = lib.core_process(len(jl), jl.ctypes.data_as(FP), h * 8, paf.ctypes.data_as(FP), 1, w * 38, 38, 3, 0)
+    rows = (np.ctypeslib.as_array(lib.core_result(), shape=(nh * 73,)).reshape(nh, 73) if nh else
+            np.zeros((0, 73), np.float32))
+    got = pkg_module("engine").humans_to_dicts(rows, w * 8, h * 8)
+    assert_humans_equal(got, want, score_tol=0.0)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import _b200_alias
+    _b200_alias.load_package()
+    import importlib
+    dist_mod = importlib.import_module(_b200_alias.PKG + ".distributed")
+    sd = net_port.he_state_dict(1234) if rank == 0 else None
+    arrays = dist_mod.broadcast_state_arrays([v.numpy() for v in sd.values()] if sd else None, device="cpu")
+    lo, hi = dist_mod.shard_range(67, rank, world)
+    q.put((rank, lo, hi, float(sum(float(a.sum()) for a in arrays[:6])), len(arrays)))
+    dist.destroy_process_group()
+
+
+def test_multi_gpu_host_logic_with_gloo():
+    """world_size-2 gloo: weights are broadcast once from rank 0, frames shard contiguously, no other collective."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=180) for _ in procs)
+    [p.join(timeout=60) for p in procs]
+    assert res[0][1:3] == (0, 34) and res[1][1:3] == (34, 67)
+    assert res[0][3] == res[1][3] and res[0][4] == res[1][4] == 184
