@@ -507,7 +507,8 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
     CU(cudaSetDevice(cuda_device));
     b200pose_post* p = new b200pose_post();
     p->device = cuda_device;
-    const long pool = (long)batch_cap * 19 * 32768 < (1L << 26) ? (long)batch_cap * 19 * 32768 : (1L << 26);
+    // candidate-key pool: 1 Mi keys (8 MB) per image of the batch, capped at 1 GiB; exhausting it sets a status bit
+    const long pool = (long)batch_cap * (1L << 20) < (1L << 27) ? (long)batch_cap * (1L << 20) : (1L << 27);
     cudaError_t e = post_alloc(p->pb, batch_cap, peak_cap, human_cap, pool);
     if (e != cudaSuccess) { delete p; return fail("post_alloc failed: %s", cudaGetErrorString(e)); }
     CU(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));

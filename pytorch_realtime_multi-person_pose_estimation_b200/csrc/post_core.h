@@ -195,6 +195,169 @@ B2P_HD void seq_std_sort(uint64_t* v, int n) {
         seq_insertion_sort(v, 0, n);
 }
 
+// ---------------------------------------------------------------- warp-parallel exact std::sort
+// One partition step of libstdc++'s introsort (__unguarded_partition_pivot: median-of-3 of first+1 / mid / last-1
+// moved to `first`, then the Hoare loop `while (comp(*lo, pivot)) ++lo; --hi; while (comp(pivot, *hi)) --hi;
+// if (!(lo < hi)) return lo; swap; ++lo`), executed by ONE WARP on 32-element chunks: the k-th position where the
+// sequential `lo` scan would stop is paired with the k-th position where the `hi` scan would stop, so the swaps -
+// and therefore the final order of elements with EQUAL keys - are exactly those of the sequential algorithm.
+// On the host (tests) the per-lane parts run as loops.  All lanes must call it with identical arguments.
+#if defined(__CUDA_ARCH__)
+#define B2P_LANE() ((int)(threadIdx.x & 31))
+#define B2P_SYNCWARP() __syncwarp()
+#else
+#define B2P_LANE() 0
+#define B2P_SYNCWARP()
+#endif
+
+B2P_HD int nth_set_bit(uint32_t m, int k) {   // position of the (k+1)-th set bit, k < popc(m)
+#if defined(__CUDA_ARCH__)
+    return (int)__fns(m, 0, k + 1);
+#else
+    for (int i = 0; i < 32; ++i)
+        if ((m >> i) & 1u) { if (k == 0) return i; --k; }
+    return -1;
+#endif
+}
+B2P_HD int popc32(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+B2P_HD uint32_t low_bits(long n) { return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)); }
+
+// stop mask for the ascending scan over positions [c, c+32): bit j <=> !(comp(v[c+j], pivot)) i.e. key >= pivot key
+B2P_HD uint32_t chunk_mask_lo(const uint64_t* v, long c, long last, uint32_t pivot) {
+#if defined(__CUDA_ARCH__)
+    const long p = c + B2P_LANE();
+    const bool stop = (p < last) && ((uint32_t)(v[p] >> 32) >= pivot);
+    return __ballot_sync(0xffffffffu, stop);
+#else
+    uint32_t m = 0;
+    for (int j = 0; j < 32; ++j) { const long p = c + j; if (p < last && (uint32_t)(v[p] >> 32) >= pivot) m |= 1u << j; }
+    return m;
+#endif
+}
+// stop mask for the descending scan over positions c-1, c-2, ..: bit j <=> position c-1-j, !(comp(pivot, v[p]))
+B2P_HD uint32_t chunk_mask_hi(const uint64_t* v, long c, long first, uint32_t pivot) {
+#if defined(__CUDA_ARCH__)
+    const long p = c - 1 - B2P_LANE();
+    const bool stop = (p >= first) && ((uint32_t)(v[p] >> 32) <= pivot);
+    return __ballot_sync(0xffffffffu, stop);
+#else
+    uint32_t m = 0;
+    for (int j = 0; j < 32; ++j) { const long p = c - 1 - j; if (p >= first && (uint32_t)(v[p] >> 32) <= pivot) m |= 1u << j; }
+    return m;
+#endif
+}
+
+B2P_HD long warp_partition(uint64_t* v, long first, long last) {
+    if (B2P_LANE() == 0) {   // __move_median_to_first(first, first+1, mid, last-1)
+        const long a = first + 1, b = first + (last - first) / 2, c = last - 1;
+        long m;
+        if (B2P_COMP(v[a], v[b])) m = B2P_COMP(v[b], v[c]) ? b : (B2P_COMP(v[a], v[c]) ? c : a);
+        else m = B2P_COMP(v[a], v[c]) ? a : (B2P_COMP(v[b], v[c]) ? c : b);
+        const uint64_t t = v[first]; v[first] = v[m]; v[m] = t;
+    }
+    B2P_SYNCWARP();
+    const uint32_t pivot = (uint32_t)(v[first] >> 32);
+    long cA = first + 1, cB = last;          // chunk A = [cA, cA+32), chunk B = positions cB-1 .. cB-32
+    uint32_t rawA = chunk_mask_lo(v, cA, last, pivot);
+    uint32_t rawB = chunk_mask_hi(v, cB, first, pivot);
+    long lo_limit = last;    // once a swap happened: the position of the last swapped `hi` (holds a lo-stop value now)
+    long hi_limit = first;   // v[first] == pivot stops the hi scan; later: position of the last swapped `lo`
+    for (;;) {
+        // effective stop masks in the CURRENT array state (rawA/rawB were loaded before the latest swaps)
+        uint32_t effA = rawA & low_bits(lo_limit - cA);
+        if (lo_limit < last && lo_limit >= cA && lo_limit < cA + 32) effA |= 1u << (lo_limit - cA);
+        uint32_t effB = rawB & low_bits(cB - 1 - hi_limit);
+        if (cB - 1 - hi_limit >= 0 && cB - 1 - hi_limit < 32) effB |= 1u << (cB - 1 - hi_limit);
+        if (effA == 0) { cA += 32; rawA = chunk_mask_lo(v, cA, last, pivot); continue; }
+        if (effB == 0) { cB -= 32; rawB = chunk_mask_hi(v, cB, first, pivot); continue; }
+        const int pa = popc32(effA), pb = popc32(effB), m = pa < pb ? pa : pb;
+        int kp = 0;              // number of leading pairs with lo_k < hi_k
+        long lo_k = 0, hi_k = 0; // of pair kp (the first failing one) or garbage if kp == m
+        long last_lo = 0, last_hi = 0;
+#if defined(__CUDA_ARCH__)
+        {
+            const int k = B2P_LANE();
+            long mylo = 0, myhi = 0;
+            bool ok = false;
+            if (k < m) {
+                mylo = cA + nth_set_bit(effA, k);
+                myhi = cB - 1 - nth_set_bit(effB, k);
+                ok = mylo < myhi;
+            }
+            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+            kp = __popc(okm);     // ok is monotone in k: lo_k increases, hi_k decreases
+            if (ok) { const uint64_t t = v[mylo]; v[mylo] = v[myhi]; v[myhi] = t; }
+            const int src_fail = kp < m ? kp : 0, src_last = kp > 0 ? kp - 1 : 0;
+            lo_k = __shfl_sync(0xffffffffu, mylo, src_fail);
+            hi_k = __shfl_sync(0xffffffffu, myhi, src_fail);
+            last_lo = __shfl_sync(0xffffffffu, mylo, src_last);
+            last_hi = __shfl_sync(0xffffffffu, myhi, src_last);
+            __syncwarp();
+        }
+#else
+        for (int k = 0; k < m; ++k) {
+            const long mylo = cA + nth_set_bit(effA, k), myhi = cB - 1 - nth_set_bit(effB, k);
+            if (!(mylo < myhi)) { lo_k = mylo; hi_k = myhi; break; }
+            const uint64_t t = v[mylo]; v[mylo] = v[myhi]; v[myhi] = t;
+            last_lo = mylo; last_hi = myhi;
+            ++kp;
+        }
+#endif
+        if (kp > 0) { lo_limit = last_hi; hi_limit = last_lo; }
+        if (kp < m) {
+            (void)hi_k;
+            // sequential loop breaks here with lo at the next lo-stop of the current state
+            return (kp > 0 && last_hi < lo_k) ? last_hi : lo_k;
+        }
+        // all m pairs swapped: the scans have passed the consumed stops
+        rawA &= ~low_bits(nth_set_bit(effA, m - 1) + 1);
+        rawB &= ~low_bits(nth_set_bit(effB, m - 1) + 1);
+    }
+}
+
+// stable insertion sort of a leaf (<= 16 elements) = what __final_insertion_sort does inside one introsort leaf
+B2P_HD void leaf_insertion_sort(uint64_t* v, long first, long last) {
+    for (long i = first + 1; i < last; ++i) {
+        const uint64_t val = v[i];
+        long j = i;
+        while (j > first && B2P_COMP(val, v[j - 1])) { v[j] = v[j - 1]; --j; }
+        v[j] = val;
+    }
+}
+
+#if !defined(__CUDA_ARCH__)
+// host reference driver of the parallel formulation (tests): same partition routine, explicit stack
+inline void par_std_sort_host(uint64_t* v, int n) {
+    if (n <= 1) return;
+    int lg = 0;
+    for (int m = n; m > 1; m >>= 1) ++lg;
+    long sf[128], sl[128];
+    int sd[128], sp = 0;
+    sf[0] = 0; sl[0] = n; sd[0] = 2 * lg; sp = 1;
+    while (sp > 0) {
+        --sp;
+        long first = sf[sp], last = sl[sp];
+        int depth = sd[sp];
+        bool heap_sorted = false;
+        while (last - first > 16) {
+            if (depth == 0) { seq_heap_sort(v, first, last); heap_sorted = true; break; }
+            --depth;
+            const long cut = warp_partition(v, first, last);
+            if (last - cut > 16) { sf[sp] = cut; sl[sp] = last; sd[sp] = depth; ++sp; }
+            else leaf_insertion_sort(v, cut, last);
+            last = cut;
+        }
+        if (!heap_sorted) leaf_insertion_sort(v, first, last);
+    }
+}
+#endif
+
 // Greedy one-to-one assignment over sorted candidates.  used_a/used_b: zeroed bitmaps.  Writes accepted
 // connections (a index, b index, score) in acceptance order; returns their number.
 B2P_HD int greedy_match(const uint64_t* keys, int n, int nb, uint32_t* used_a, uint32_t* used_b, int max_conn,

@@ -170,11 +170,145 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
     return res;
 }
 
+// Exact std::sort (libstdc++ introsort) of `n` keys by the whole block: ranges live on a small shared stack plus
+// per-warp local stacks; each warp pops a range, partitions it with warp_partition() (exact emulation of the
+// sequential Hoare loop), publishes the right part for other warps and keeps the left part.  Parts of <= 16 elements
+// are insertion-sorted in place - together that is exactly __introsort_loop + __final_insertion_sort.
+constexpr int kSortQ = 64, kSortLocal = 48, kLimbWarps = kLimbThreads / 32;
+struct SortShared {
+    int lock, top, pending;
+    int sf[kSortQ], sl[kSortQ], sd[kSortQ];
+    int ltop[kLimbWarps];
+    int lf[kLimbWarps][kSortLocal], ll[kLimbWarps][kSortLocal], ld[kLimbWarps][kSortLocal];
+};
+
+__device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { sh.lock = 0; sh.top = 0; sh.pending = 0; }
+    if (tid < kLimbWarps) sh.ltop[tid] = 0;
+    __syncthreads();
+    if (n <= 16) {
+        if (tid == 0) leaf_insertion_sort(v, 0, n);
+        __syncthreads();
+        return;
+    }
+    if (tid == 0) {
+        int lg = 0;
+        for (int m = n; m > 1; m >>= 1) ++lg;
+        sh.sf[0] = 0; sh.sl[0] = n; sh.sd[0] = 2 * lg; sh.top = 1; sh.pending = 1;
+    }
+    __syncthreads();
+    unsigned idle = 0;
+    for (;;) {
+        int f = 0, l = 0, d = 0, state = 0;    // state: 0 nothing yet, 1 got a range, 2 all done
+        if (lane == 0) {
+            if (sh.ltop[warp] > 0) {
+                const int t = --sh.ltop[warp];
+                f = sh.lf[warp][t]; l = sh.ll[warp][t]; d = sh.ld[warp][t]; state = 1;
+            } else {
+                while (atomicCAS(&sh.lock, 0, 1) != 0) {}
+                if (sh.top > 0) {
+                    const int t = --sh.top;
+                    f = sh.sf[t]; l = sh.sl[t]; d = sh.sd[t]; state = 1;
+                }
+                __threadfence_block();
+                atomicExch(&sh.lock, 0);
+                if (state == 0 && atomicAdd(&sh.pending, 0) == 0) state = 2;
+            }
+        }
+        state = __shfl_sync(0xffffffffu, state, 0);
+        if (state == 2) break;
+        if (state == 0) {
+            if (++idle > (1u << 24)) { printf("[b200pose] exact sort: idle watchdog (block %d,%d)\n", (int)blockIdx.x, (int)blockIdx.y); __trap(); }
+            __nanosleep(200);
+            continue;
+        }
+        idle = 0;
+        f = __shfl_sync(0xffffffffu, f, 0);
+        l = __shfl_sync(0xffffffffu, l, 0);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        __threadfence();                       // see the swaps of the warp that published this range
+        bool heap_sorted = false;
+        while (l - f > 16) {
+            if (d == 0) {                      // depth limit exhausted: std::__partial_sort == heap sort
+                if (lane == 0) seq_heap_sort(v, f, l);
+                __syncwarp();
+                heap_sorted = true;
+                break;
+            }
+            --d;
+            const int cut = (int)warp_partition(v, f, l);
+            if (l - cut > 16) {
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(&sh.pending, 1);
+                    bool pushed = false;
+                    while (atomicCAS(&sh.lock, 0, 1) != 0) {}
+                    if (sh.top < kSortQ) { const int t = sh.top++; sh.sf[t] = cut; sh.sl[t] = l; sh.sd[t] = d; pushed = true; }
+                    __threadfence_block();
+                    atomicExch(&sh.lock, 0);
+                    if (!pushed) {
+                        const int t = sh.ltop[warp]++;     // depth <= 2*log2(n) <= 2*31 > kSortLocal only for absurd n
+                        if (t < kSortLocal) { sh.lf[warp][t] = cut; sh.ll[warp][t] = l; sh.ld[warp][t] = d; }
+                        else { sh.ltop[warp] = kSortLocal; atomicSub(&sh.pending, 1); }   // unreachable for n < 2^24
+                    }
+                }
+            } else if (lane == 1) {
+                leaf_insertion_sort(v, cut, l);
+            }
+            l = cut;
+            __syncwarp();
+        }
+        if (!heap_sorted && lane == 0) leaf_insertion_sort(v, f, l);
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicSub(&sh.pending, 1); }
+    }
+    __syncthreads();
+}
+
+// Greedy one-to-one assignment (pafprocess.cpp:98-124) by one warp, 32 sorted candidates per step; conflicts inside
+// a chunk are resolved in candidate order, so the result equals the sequential loop.
+__device__ int greedy_match_warp(const uint64_t* keys, int n, int nb, uint32_t* used_a, uint32_t* used_b, int max_conn,
+                                 int* conn_a, int* conn_b, float* conn_s) {
+    const int lane = threadIdx.x & 31;
+    int nc = 0;
+    for (int base = 0; base < n && nc < max_conn; base += 32) {
+        const int i = base + lane;
+        uint64_t k = 0;
+        int a = -1, b = -1;
+        bool free_ = false;
+        if (i < n) {
+            k = keys[i];
+            const uint32_t pair = (uint32_t)k;
+            a = pair / nb;
+            b = pair - a * nb;
+            free_ = !((used_a[a >> 5] >> (a & 31)) & 1u) && !((used_b[b >> 5] >> (b & 31)) & 1u);
+        }
+        uint32_t active = __ballot_sync(0xffffffffu, free_);
+        while (active && nc < max_conn) {
+            const int leader = __ffs(active) - 1;
+            const int la = __shfl_sync(0xffffffffu, a, leader), lb = __shfl_sync(0xffffffffu, b, leader);
+            if (lane == leader) {
+                used_a[a >> 5] |= 1u << (a & 31);
+                used_b[b >> 5] |= 1u << (b & 31);
+                conn_a[nc] = a;
+                conn_b[nc] = b;
+                conn_s[nc] = key_score(k);
+            }
+            ++nc;
+            active &= ~__ballot_sync(0xffffffffu, a == la || b == lb);
+        }
+        __syncwarp();
+    }
+    return nc;
+}
+
 __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up) {
     extern __shared__ unsigned long long sm_keys[];       // [cand_smem_cap]
     __shared__ uint32_t used_a[64], used_b[64];            // peak_cap <= 2048
     __shared__ int scan_scratch[kLimbThreads / 32 + 1];
     __shared__ long s_pool_base;
+    __shared__ SortShared s_sort;
     const int limb = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
     const int pa = c_limb_parts[limb][0], pbp = c_limb_parts[limb][1];
     const int c1 = c_limb_paf[limb][0], c2 = c_limb_paf[limb][1];
@@ -196,6 +330,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     const int per = (npairs + kLimbThreads - 1) / kLimbThreads;
     const int p_begin = min(npairs, tid * per), p_end = min(npairs, p_begin + per);
 
+    // pass 1: count the candidates of this thread's contiguous slice of (a, b) pairs
     int cnt = 0;
     for (int p = p_begin; p < p_end; ++p) {
         const int a = p / nb, b = p - a * nb;
@@ -203,18 +338,16 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
         if (pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &s)) ++cnt;
     }
     int n;
-    const int off0 = block_exclusive_scan(cnt, &n, scan_scratch);
+    int off = block_exclusive_scan(cnt, &n, scan_scratch);
     if (n == 0) {
         if (tid == 0) *out_cnt = 0;
         return;
     }
-    int npow2 = 1;
-    while (npow2 < n) npow2 <<= 1;
     unsigned long long* keys = sm_keys;
-    if (npow2 > pb.cand_smem_cap) {
-        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, (unsigned long long)npow2);
+    if (n > pb.cand_smem_cap) {
+        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, (unsigned long long)n);
         __syncthreads();
-        if (s_pool_base + npow2 > pb.pool_cap) {
+        if (s_pool_base + n > pb.pool_cap) {
             if (tid == 0) {
                 atomicOr(&pb.status[img], 2);
                 *out_cnt = 0;
@@ -223,48 +356,21 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
         }
         keys = pb.pool + s_pool_base;
     }
-    for (int pass = 0; pass < 2; ++pass) {
-        // pass 0: keys in generation order -> parallel sort; pass 1 (only if equal scores exist): regenerate in
-        // generation order and reproduce std::sort's permutation sequentially.
-        int off = off0;
-        for (int p = p_begin; p < p_end; ++p) {
-            const int a = p / nb, b = p - a * nb;
-            float s;
-            if (pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &s)) keys[off++] = cand_key(s, (uint32_t)p);
-        }
-        if (pass == 1) {
-            __syncthreads();
-            if (tid == 0) {
-                seq_std_sort(reinterpret_cast<uint64_t*>(keys), n);
-                atomicAdd(&pb.status[img], 256);
-            }
-            __syncthreads();
-            break;
-        }
-        for (int i = n + tid; i < npow2; i += kLimbThreads) keys[i] = ~0ull;
-        __syncthreads();
-        for (int k = 2; k <= npow2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < npow2; i += kLimbThreads) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const unsigned long long x = keys[i], y = keys[ixj];
-                        const bool asc = (i & k) == 0;
-                        if ((x > y) == asc) { keys[i] = y; keys[ixj] = x; }
-                    }
-                }
-                __syncthreads();
-            }
-        int tie = 0;
-        for (int i = tid; i + 1 < n; i += kLimbThreads) tie |= ((keys[i] >> 32) == (keys[i + 1] >> 32));
-        if (!__syncthreads_or(tie)) break;
+    // pass 2: keys in generation order (a-major, b-minor) = the order the reference pushes candidates in
+    for (int p = p_begin; p < p_end; ++p) {
+        const int a = p / nb, b = p - a * nb;
+        float s;
+        if (pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &s)) keys[off++] = cand_key(s, (uint32_t)p);
     }
     for (int i = tid; i < 64; i += kLimbThreads) { used_a[i] = 0; used_b[i] = 0; }
+    __threadfence();
     __syncthreads();
-    if (tid == 0) {
+    block_exact_sort(reinterpret_cast<uint64_t*>(keys), n, s_sort);     // std::sort, pafprocess.cpp:97
+    if (tid < 32) {
         const long o = ((long)img * kNumLimb + limb) * cap;
-        *out_cnt = greedy_match(reinterpret_cast<const uint64_t*>(keys), n, nb, used_a, used_b, min(na, nb),
-                                pb.conn_a + o, pb.conn_b + o, pb.conn_s + o);
+        const int nc = greedy_match_warp(reinterpret_cast<const uint64_t*>(keys), n, nb, used_a, used_b, min(na, nb),
+                                         pb.conn_a + o, pb.conn_b + o, pb.conn_s + o);
+        if (tid == 0) *out_cnt = nc;
     }
 }
 

@@ -13,7 +13,7 @@ static const int LIMB_PARTS[19][2] = B2P_LIMB_TABLES;
 static const int LIMB_PAF[19][2] = B2P_LIMB_PAF_TABLES;
 
 static std::vector<float> g_out;   // per human: score, then 18 x (x, y, peak score, cid)  (cid < 0 = missing)
-static int g_degraded = 0, g_ties = 0;
+static int g_degraded = 0, g_ties = 0, g_sort_mismatch = 0;
 
 extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by part*/, int h_up, const float* paf,
                             long sc, long sy, long sx, int shift, int list_cap_stress) {
@@ -41,6 +41,7 @@ extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by p
     std::vector<int> ca[19], cb[19];
     std::vector<float> cs[19];
     g_ties = 0;
+    g_sort_mismatch = 0;
     int total_conn = 0;
     for (int l = 0; l < 19; ++l) {
         const int pa = LIMB_PARTS[l][0], pb = LIMB_PARTS[l][1];
@@ -58,10 +59,14 @@ extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by p
         bool ties = false;
         for (size_t i = 0; i + 1 < sorted.size(); ++i)
             if ((sorted[i] >> 32) == (sorted[i + 1] >> 32)) ties = true;
-        if (ties) {
-            ++g_ties;
-            sorted = keys;
-            seq_std_sort(sorted.data(), (int)sorted.size());
+        if (ties) ++g_ties;
+        {   // the product always runs the exact std::sort emulation; check both formulations agree
+            std::vector<uint64_t> seq = keys, par = keys;
+            seq_std_sort(seq.data(), (int)seq.size());
+            par_std_sort_host(par.data(), (int)par.size());
+            if (seq != par) ++g_sort_mismatch;
+            if (!ties && seq != sorted) ++g_sort_mismatch;   // without ties every correct sort gives this order
+            sorted = par;
         }
         const int maxc = na < nb ? na : nb;
         std::vector<uint32_t> ua((na + 31) / 32, 0), ub((nb + 31) / 32, 0);
@@ -101,3 +106,12 @@ extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by p
 extern "C" const float* core_result() { return g_out.data(); }
 extern "C" int core_degraded() { return g_degraded; }
 extern "C" int core_ties() { return g_ties; }
+extern "C" int core_sort_mismatch() { return g_sort_mismatch; }
+// direct test hook: sort `n` keys with both formulations, return 0 when identical
+extern "C" int core_sort_check(uint64_t* keys, int n, uint64_t* out) {
+    std::vector<uint64_t> seq(keys, keys + n), par(keys, keys + n);
+    seq_std_sort(seq.data(), n);
+    par_std_sort_host(par.data(), n);
+    for (int i = 0; i < n; ++i) out[i] = par[i];
+    return seq == par ? 0 : 1;
+}

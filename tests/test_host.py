@@ -126,6 +126,7 @@ def test_device_cores_on_host_match_oracle(name, built):
             np.zeros((0, 73), np.float32))
     got = pkg_module("engine").humans_to_dicts(rows, w * 8, h * 8)
     assert_humans_equal(got, want, score_tol=0.0)
+    assert lib.core_sort_mismatch() == 0      # warp-chunked partition == sequential std::sort emulation
 
 
 def _gloo_worker(rank, world, port, q):
@@ -156,3 +157,27 @@ def test_multi_gpu_host_logic_with_gloo():
     [p.join(timeout=60) for p in procs]
     assert res[0][1:3] == (0, 34) and res[1][1:3] == (34, 67)
     assert res[0][3] == res[1][3] and res[0][4] == res[1][4] == 184
+
+
+def test_warp_partition_reproduces_std_sort(built):
+    """The chunked (32-wide) Hoare partition the GPU runs gives the same permutation as the sequential libstdc++
+    introsort restatement, including the order of equal keys, on duplicate-heavy and adversarial inputs."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "build", "libpostcore_host.so"))
+    U = ctypes.POINTER(ctypes.c_uint64)
+    lib.core_sort_check.argtypes = [U, ctypes.c_int, U]
+    rs = np.random.RandomState(0)
+    def check(hi):
+        n = len(hi)
+        keys = (hi.astype(np.uint64) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+        out = np.zeros(max(n, 1), np.uint64)
+        assert lib.core_sort_check(keys.ctypes.data_as(U), n, out.ctypes.data_as(U)) == 0
+        out = out[:n]
+        assert np.all((out[:-1] >> np.uint64(32)) <= (out[1:] >> np.uint64(32)))
+        assert sorted(out.tolist()) == sorted(keys.tolist())
+    for n in list(range(0, 40)) + [63, 64, 65, 100, 257, 1000, 4097, 30000]:
+        for distinct in (1, 2, 7, max(1, n // 3), 1 << 30):
+            check(rs.randint(0, distinct, size=n))
+    for n in (17, 33, 100, 1000, 5000):
+        for hi in (np.arange(n), np.arange(n)[::-1], np.minimum(np.arange(n), np.arange(n)[::-1]), np.arange(n) % 2,
+                   np.arange(n) % 17):
+            check(np.ascontiguousarray(hi))
