@@ -225,8 +225,22 @@ def cpu_frame_fn():
     C pafprocess (oracle/_ref when it was built from the reference sources, else the plain-C port)."""
     import torch
     from oracle import glue_port, net_port, pafprocess_oracle
-    torch.set_num_threads(os.cpu_count())
     sd = net_port.he_state_dict(1234)
+    # "all the host threads it can use": torch's default is one thread per logical CPU; on many-core hosts the
+    # conv stack is faster with fewer, so the best of {all, half, quarter} logical CPUs is used and reported.
+    best = None
+    probe = torch.rand((1, 3, H, W), generator=torch.Generator().manual_seed(1)) - 0.5
+    for nt in sorted({os.cpu_count(), max(1, os.cpu_count() // 2), max(1, os.cpu_count() // 4)}, reverse=True):
+        torch.set_num_threads(nt)
+        with torch.no_grad():
+            net_port.forward(sd, probe)
+            t0 = time.perf_counter()
+            net_port.forward(sd, probe)
+            dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    torch.set_num_threads(best[1])
+    cpu_frame_fn.threads = best[1]
     if pafprocess_oracle.have_ref():
         paf_lib, kind = pafprocess_oracle.load_ref(), "reference pafprocess.cpp + oracle port of the torch/numpy glue"
     else:
@@ -250,7 +264,7 @@ def cpu_baseline_sample(frames=2):
     for _ in range(frames):
         one_frame()
     dt = time.perf_counter() - t0
-    return {"value": round(frames / dt, 4), "unit": UNIT, "cores": os.cpu_count(),
+    return {"value": round(frames / dt, 4), "unit": UNIT, "cores": getattr(cpu_frame_fn, "threads", os.cpu_count()),
             "kind": "port" if kind == "port" else "reference",
             "sample": "%d frames of 368x368, batch 1, serial run_eval-style loop (%s), after 1 warm-up frame" % (frames, kind)}
 
@@ -273,7 +287,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "batch=32 per GPU, 368x368, rtpose VGG19 + pafprocess; each step = a bounded sample "
                                    "of %d frame(s) run serially at batch 1 on the host CPU" % per_step},
-            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count(),
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": getattr(cpu_frame_fn, "threads", os.cpu_count()),
                              "kind": "port" if kind == "port" else "reference",
                              "sample": "%d frame(s) per step, %d steps (%s)" % (per_step, args.steps, kind)},
             "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

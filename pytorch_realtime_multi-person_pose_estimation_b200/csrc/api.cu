@@ -532,11 +532,11 @@ static int post_run_dev(b200pose_post* p, const float* d_heat, const float* d_pa
     if (layout == 0) {
         e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, (long)h * w, w, 1, h, w, thresh, st);
         if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
-        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, (long)h * w, w, 1, 3, h * 8, st);
+        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, (long)h * w, w, 1, 3, h * 8, w, h, st);
     } else {
         e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, 1, (long)w * 19, 19, h, w, thresh, st);
         if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
-        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, 1, (long)w * 38, 38, 3, h * 8, st);
+        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, 1, (long)w * 38, 38, 3, h * 8, w, h, st);
     }
     if (e != cudaSuccess) return fail("post_limbs_and_assemble: %s", cudaGetErrorString(e));
     g_launches += 3;
@@ -697,7 +697,7 @@ int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, fl
     CU(cudaMemcpyAsync(pb.peak_s, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, st));
     CU(p->d_paf.ensure((size_t)f1 * f2 * f3));
     CU(cudaMemcpyAsync(p->d_paf.p, pafmap, (size_t)f1 * f2 * f3 * 4, cudaMemcpyHostToDevice, st));
-    cudaError_t e = post_limbs_and_assemble(pb, 1, p->d_paf.p, 0, 1, (long)f2 * f3, f3, 0, h1, st);
+    cudaError_t e = post_limbs_and_assemble(pb, 1, p->d_paf.p, 0, 1, (long)f2 * f3, f3, 0, h1, f2, f1, st);
     if (e != cudaSuccess) return fail("post_limbs_and_assemble: %s", cudaGetErrorString(e));
     g_launches += 2;
     p->last_n = 1; p->fetched = false; p->last_stream = st;

@@ -27,6 +27,7 @@ constexpr int kLimbThreads = 512;
 constexpr int kAsmThreads = 128;
 constexpr int kHorStride = 40;   // (2*2+1) * 8
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ------------------------------------------------------------------ peaks
@@ -182,6 +183,25 @@ struct SortShared {
     int lf[kLimbWarps][kSortLocal], ll[kLimbWarps][kSortLocal], ld[kLimbWarps][kSortLocal];
 };
 
+// Stable sort of up to two leaves (<= 16 keys each) by one warp: lanes 0-15 take leaf 0, lanes 16-31 leaf 1; every key's
+// final slot is its stable rank (#smaller + #equal-before), which is what insertion sort produces.
+__device__ __forceinline__ void warp_sort_two_leaves(uint64_t* v, long f0, long l0, long f1, long l1) {
+    const int lane = threadIdx.x & 31, h = lane >> 4, j = lane & 15;
+    const long f = h ? f1 : f0;
+    const int n = (int)(h ? l1 - f1 : l0 - f0);
+    const uint64_t key = (j < n) ? v[f + j] : ~0ull;
+    const uint32_t mh = (uint32_t)(key >> 32);
+    int rank = 0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const uint64_t other = __shfl_sync(0xffffffffu, key, (h << 4) | t);
+        const uint32_t oh = (uint32_t)(other >> 32);
+        if (t < n && (oh < mh || (oh == mh && t < j))) ++rank;
+    }
+    if (j < n) v[f + rank] = key;
+    __syncwarp();
+}
+
 __device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { sh.lock = 0; sh.top = 0; sh.pending = 0; }
@@ -253,13 +273,13 @@ __device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh) {
                         else { sh.ltop[warp] = kSortLocal; atomicSub(&sh.pending, 1); }   // unreachable for n < 2^24
                     }
                 }
-            } else if (lane == 1) {
-                leaf_insertion_sort(v, cut, l);
+            } else {
+                warp_sort_two_leaves(v, cut, l, 0, 0);
             }
             l = cut;
             __syncwarp();
         }
-        if (!heap_sorted && lane == 0) leaf_insertion_sort(v, f, l);
+        if (!heap_sorted) warp_sort_two_leaves(v, f, l, 0, 0);
         __syncwarp();
         if (lane == 0) { __threadfence(); atomicSub(&sh.pending, 1); }
     }
@@ -303,15 +323,15 @@ __device__ int greedy_match_warp(const uint64_t* keys, int n, int nb, uint32_t* 
     return nc;
 }
 
-__global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up) {
-    extern __shared__ unsigned long long sm_keys[];       // [cand_smem_cap]
+__global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up, int lw,
+                                                             int lh, int paf_in_smem) {
+    extern __shared__ unsigned long long sm_keys[];       // [cand_smem_cap] keys, then (optionally) 2 PAF planes
     __shared__ uint32_t used_a[64], used_b[64];            // peak_cap <= 2048
     __shared__ int scan_scratch[kLimbThreads / 32 + 1];
     __shared__ long s_pool_base;
     __shared__ SortShared s_sort;
     const int limb = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
     const int pa = c_limb_parts[limb][0], pbp = c_limb_parts[limb][1];
-    const int c1 = c_limb_paf[limb][0], c2 = c_limb_paf[limb][1];
     const int cap = pb.peak_cap;
     const int na = pb.counts[img * kNumPart + pa], nb = pb.counts[img * kNumPart + pbp];
     int* out_cnt = pb.conn_cnt + img * kNumLimb + limb;
@@ -325,6 +345,20 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     const int* by = pb.peak_y + ((long)img * kNumPart + pbp) * cap;
     PafView paf = paf0;
     paf.base += img * p_img;
+    int c1 = c_limb_paf[limb][0], c2 = c_limb_paf[limb][1];
+    if (paf_in_smem) {
+        // the 10 x na x nb line-integral samples of this limb hit only its two PAF planes (2 x h x w floats):
+        // stage them in shared memory once instead of gathering from L2 ~1e6 times
+        float* planes = reinterpret_cast<float*>(sm_keys + pb.cand_smem_cap);
+        const int hw = lw * lh;
+        for (int i = tid; i < 2 * hw; i += kLimbThreads) {
+            const int ch = i >= hw, r = i - ch * hw;
+            planes[i] = paf.base[(ch ? c2 : c1) * paf.sc + (long)(r / lw) * paf.sy + (long)(r % lw) * paf.sx];
+        }
+        __syncthreads();
+        paf.base = planes; paf.sc = hw; paf.sy = lw; paf.sx = 1;
+        c1 = 0; c2 = 1;
+    }
 
     const int npairs = na * nb;
     const int per = (npairs + kLimbThreads - 1) / kLimbThreads;
@@ -407,26 +441,53 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(PostBuffers pb) {
     __syncthreads();
 
     float* rows = pb.rows + (long)img * pb.row_cap * kRowFloats;
+    __shared__ Assembler s_as;
     if (tid == 0) {
-        Assembler as;
-        as.rows = rows;
-        as.alive = alive;
-        as.lists = pb.lists + (long)img * id_cap * kListCap;
-        as.list_n = list_n;
-        as.part_base = part_base;
-        as.peak_score = id_score;
-        as.row_cap = pb.row_cap;
-        as.nrows = 0;
-        as.degraded = 0;
-        as.overflow = 0;
-        for (int l = 0; l < kNumLimb; ++l) {
-            const int p1 = c_limb_parts[l][0], p2 = c_limb_parts[l][1];
-            const int nc = pb.conn_cnt[img * kNumLimb + l];
-            const long o = ((long)img * kNumLimb + l) * cap;
-            for (int c = 0; c < nc; ++c)
-                as.add_connection(l, p1, p2, part_base[p1] + pb.conn_a[o + c], part_base[p2] + pb.conn_b[o + c],
-                                  pb.conn_s[o + c]);
+        s_as.rows = rows;
+        s_as.alive = alive;
+        s_as.lists = pb.lists + (long)img * id_cap * kListCap;
+        s_as.list_n = list_n;
+        s_as.part_base = part_base;
+        s_as.peak_score = id_score;
+        s_as.row_cap = pb.row_cap;
+        s_as.nrows = 0;
+        s_as.degraded = 0;
+        s_as.overflow = 0;
+    }
+    __syncthreads();
+    // The assembly itself is inherently sequential (pafprocess.cpp:127-185) and latency bound: one thread walks the
+    // connections.  Before each limb all threads pull the lines that walk will touch (row lists of both end points,
+    // the listed rows, peak scores) into L1 so the sequential part runs on L1 hits.
+    for (int l = 0; l < kNumLimb; ++l) {
+        const int p1 = c_limb_parts[l][0], p2 = c_limb_parts[l][1];
+        const int nc = pb.conn_cnt[img * kNumLimb + l];
+        const long o = ((long)img * kNumLimb + l) * cap;
+        for (int c = tid; c < nc; c += kAsmThreads) {
+            const int ids[2] = {part_base[p1] + pb.conn_a[o + c], part_base[p2] + pb.conn_b[o + c]};
+            prefetch_l1(pb.conn_s + o + c);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int id = ids[e];
+                prefetch_l1(id_score + id);
+                const int n = s_as.list_n[id];
+                for (int i = 0; i < n && i < kListCap; ++i) {
+                    const int r = s_as.lists[id * kListCap + i];
+                    prefetch_l1(rows + (long)r * kRowFloats);
+                    prefetch_l1(rows + (long)r * kRowFloats + kRowFloats - 1);
+                    prefetch_l1(alive + r);
+                }
+            }
         }
+        __syncthreads();
+        if (tid == 0) {
+            for (int c = 0; c < nc; ++c)
+                s_as.add_connection(l, p1, p2, part_base[p1] + pb.conn_a[o + c], part_base[p2] + pb.conn_b[o + c],
+                                    pb.conn_s[o + c]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        Assembler& as = s_as;
         int nh = 0, st = 0;
         for (int r = 0; r < as.nrows; ++r)
             if (as.keep(r)) {
@@ -525,12 +586,22 @@ cudaError_t post_peaks(const PostBuffers& pb, int batch, const float* heat, long
 }
 
 cudaError_t post_limbs_and_assemble(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
-                                    long p_x, int shift, int h_up, cudaStream_t s) {
+                                    long p_x, int shift, int h_up, int lw, int lh, cudaStream_t s) {
     if (batch > pb.batch_cap) return cudaErrorInvalidValue;
     B2P_TRY(cudaMemsetAsync(pb.pool_cursor, 0, sizeof(unsigned long long), s));
     PafView pv{paf, p_ch, p_y, p_x, shift};
-    limbs_kernel<<<dim3(kNumLimb, batch), kLimbThreads, pb.cand_smem_cap * sizeof(unsigned long long), s>>>(pb, pv, p_img,
-                                                                                                           h_up);
+    size_t smem = pb.cand_smem_cap * sizeof(unsigned long long);
+    int in_smem = 0;
+    if (shift == 3 && (size_t)2 * lw * lh * sizeof(float) <= 96 * 1024) {
+        in_smem = 1;
+        smem += (size_t)2 * lw * lh * sizeof(float);
+    }
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        B2P_TRY(cudaFuncSetAttribute(limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    limbs_kernel<<<dim3(kNumLimb, batch), kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem);
     B2P_TRY(cudaGetLastError());
     assemble_kernel<<<batch, kAsmThreads, pb.human_cap * sizeof(int), s>>>(pb);
     return cudaGetLastError();

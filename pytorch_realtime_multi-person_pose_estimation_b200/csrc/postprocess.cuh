@@ -52,6 +52,7 @@ cudaError_t post_peaks(const PostBuffers& pb, int batch, const float* heat, long
                        int h, int w, float thresh, cudaStream_t s);
 // paf: fp32 view per image: base + img*p_img, strides (p_ch, p_y, p_x), shift (3: low-res, 0: already upsampled).
 cudaError_t post_limbs_and_assemble(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
-                                    long p_x, int shift, int h_up, cudaStream_t s);
+                                    long p_x, int shift, int h_up, int lw, int lh, cudaStream_t s);
+// lw x lh: dimensions of the low-resolution PAF planes (used to stage them in shared memory when shift == 3)
 
 }  // namespace b2p
