@@ -74,6 +74,9 @@ int b200pose_post_run(b200pose_post* post, const float* heat, const float* paf, 
                       int w, float thresh, void* cuda_stream);
 /* Blocks until the stream work of the last run finished and results are on the host. */
 int b200pose_post_sync(b200pose_post* post);
+/* Diagnostics: out[0..2] = max SM cycles of the limbs kernel phases (scoring, exact sort, greedy) over all blocks since
+ * the last reset, out[3] = max candidates of a limb, out[4] = total candidates. */
+int b200pose_post_debug(b200pose_post* post, unsigned long long* out, int n, int reset);
 int b200pose_post_num_humans(b200pose_post* post, int img);             /* < 0 on error */
 int b200pose_post_status(b200pose_post* post, int img);                 /* status bits of the last run */
 int b200pose_post_get_humans(b200pose_post* post, int img, float* out, int max_humans);   /* returns count */

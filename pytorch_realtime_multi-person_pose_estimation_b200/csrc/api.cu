@@ -587,6 +587,12 @@ int b200pose_post_sync(b200pose_post* p) {
     return 0;
 }
 
+int b200pose_post_debug(b200pose_post* p, unsigned long long* out, int n, int reset) {
+    if (!p || n > 16) return -1;
+    if (cudaMemcpy(out, p->pb.dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(p->pb.dbg, 0, 16 * sizeof(unsigned long long));
+    return 0;
+}
 int b200pose_post_num_humans(b200pose_post* p, int img) {
     if (b200pose_post_sync(p)) return -1;
     if (img < 0 || img >= p->last_n) return -1;

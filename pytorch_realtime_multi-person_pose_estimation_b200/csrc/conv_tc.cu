@@ -138,42 +138,55 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
         }
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        if (lane == 0) {
+        // The whole warp walks the loops (warp-uniform control flow, uniform registers for the descriptors); one
+        // elected lane issues the tcgen05 instructions.  A divergent `if (lane == 0)` around the loop makes ptxas wrap
+        // every UTCHMMA in an ELECT/BRA.U.ANY uniformisation loop (~2x the issue cost).
+        {
             const uint32_t idesc = make_idesc_bf16_m128(a.n_tile);
-            const uint32_t patch_addr0 = smem_u32(patch_smem);
-            const uint32_t b_addr0 = smem_u32(b_smem);
+            // Descriptors are built incrementally: the high words are loop invariants, the low word (address >> 4)
+            // only receives small adds per tap / sub-tile / K step.
+            const uint64_t adesc_hi = make_sdesc_sw128(0, kPatchPitch * 128, 0);
+            const uint64_t bdesc_hi = make_sdesc_sw128(0, 1024, 0);
+            const uint32_t patch_lo0 = (smem_u32(patch_smem) & 0x3FFFFu) >> 4;
+            const uint32_t b_lo0 = (smem_u32(b_smem) & 0x3FFFFu) >> 4;
+            const uint32_t row_wrap = (kPatchPitch - a.ksize) * 8;     // (16-byte units) jump to the next filter row
             uint32_t pi = 0, pph = 0, bi = 0, bph = 0, ai = 0, aph = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 mbar_wait(&acc_empty[ai], aph ^ 1, 3);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + ai * 256;
+                uint32_t accumulate = 0;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
                     mbar_wait(&patch_full[pi], pph, 4);
-                    const uint32_t patch_addr = patch_addr0 + pi * kPatchBytes;
-                    int dy = 0, dx = 0;
+                    uint32_t a_lo = patch_lo0 + pi * (kPatchBytes >> 4);     // window start of tap (0,0), sub-tile 0
+                    int dx = 0;
                     for (int tap = 0; tap < taps; ++tap) {
                         mbar_wait(&b_full[bi], bph, 5);
                         tc_fence_after();
-                        const uint32_t b_addr = b_addr0 + bi * kBStageBytes;
-                        const uint32_t boff = a.use_base_offset ? (dx & 7) : 0;
+                        const uint32_t b_lo = b_lo0 + bi * (kBStageBytes >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int sub = 0; sub < 2; ++sub) {
-                            const uint32_t a_addr = patch_addr + (dy * kPatchPitch + dx + sub * 8) * 128;
+                            for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, kPatchPitch * 128, boff);
-                                const uint64_t bdesc = make_sdesc_sw128(b_addr + k * 32, 1024, 0);
-                                umma_bf16(d_tmem + sub * 128, adesc, bdesc, idesc, (cb | tap | k) != 0);
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
+                                              bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
+                                }
+                            }
+                            umma_commit(&b_empty[bi]);
+                            if (tap == taps - 1) {
+                                umma_commit(&patch_empty[pi]);
+                                if (cb == a.cin_blocks - 1) umma_commit(&acc_full[ai]);
                             }
                         }
-                        umma_commit(&b_empty[bi]);
+                        __syncwarp();
+                        accumulate = 1;
                         if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
-                        if (++dx == a.ksize) { dx = 0; ++dy; }
+                        a_lo += 8;                                            // next tap: one pixel (128 B) to the right
+                        if (++dx == a.ksize) { dx = 0; a_lo += row_wrap; }
                     }
-                    umma_commit(&patch_empty[pi]);
                     if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; }
                 }
-                umma_commit(&acc_full[ai]);
                 if (++ai == 2) { ai = 0; aph ^= 1; }
             }
         }

@@ -321,6 +321,99 @@ B2P_HD long warp_partition(uint64_t* v, long first, long last) {
     }
 }
 
+// ---------------------------------------------------------------- block-parallel exact partition (big ranges)
+// Same pairing rule as warp_partition, evaluated by ranks instead of by scanning: with lo-stops (key >= pivot) ranked
+// from the left and hi-stops (key <= pivot) ranked from the right over [first+1, last), the sequential Hoare loop
+// swaps lo-stop #k with hi-stop #k for k = 1..K, K = number of k with posA[k] < posB[k] (monotone), and returns
+// min(posA[K+1], posB[K]).  T cooperating threads each own a contiguous slice; phases are separated by block
+// barriers on the device and by plain loops on the host (tests).
+struct BlockPartState {
+    long first, last;
+    uint32_t pivot;
+    long per;
+    int totA, totB, K;
+    long cut;
+};
+B2P_HD void bp_prepare(BlockPartState& st, uint64_t* v, long first, long last, int T) {   // one thread
+    const long a = first + 1, b = first + (last - first) / 2, c = last - 1;
+    long m;
+    if (B2P_COMP(v[a], v[b])) m = B2P_COMP(v[b], v[c]) ? b : (B2P_COMP(v[a], v[c]) ? c : a);
+    else m = B2P_COMP(v[a], v[c]) ? a : (B2P_COMP(v[b], v[c]) ? c : b);
+    const uint64_t t = v[first]; v[first] = v[m]; v[m] = t;
+    st.first = first; st.last = last;
+    st.pivot = (uint32_t)(v[first] >> 32);
+    st.per = (last - first - 1 + T - 1) / T;
+}
+B2P_HD void bp_slice(const BlockPartState& st, int tid, long* s, long* e) {
+    long b = st.first + 1 + (long)tid * st.per;
+    if (b > st.last) b = st.last;
+    long en = b + st.per;
+    if (en > st.last) en = st.last;
+    *s = b; *e = en;
+}
+B2P_HD void bp_count(const BlockPartState& st, const uint64_t* v, int tid, int* cA, int* cB) {
+    long s, e;
+    bp_slice(st, tid, &s, &e);
+    int a = 0, b = 0;
+    for (long p = s; p < e; ++p) {
+        const uint32_t k = (uint32_t)(v[p] >> 32);
+        a += (k >= st.pivot);
+        b += (k <= st.pivot);
+    }
+    *cA = a; *cB = b;
+}
+// offA: lo-stops before this slice; b_right: hi-stops after this slice.  posA/posB are 1-based rank -> position.
+B2P_HD void bp_scatter(const BlockPartState& st, const uint64_t* v, int tid, int offA, int b_right, int32_t* posA,
+                       int32_t* posB) {
+    long s, e;
+    bp_slice(st, tid, &s, &e);
+    int a = offA;
+    for (long p = s; p < e; ++p)
+        if ((uint32_t)(v[p] >> 32) >= st.pivot) posA[++a] = (int32_t)p;
+    int b = b_right;
+    for (long p = e - 1; p >= s; --p)
+        if ((uint32_t)(v[p] >> 32) <= st.pivot) posB[++b] = (int32_t)p;
+}
+B2P_HD int bp_count_swaps(const BlockPartState& st, int tid, int T, const int32_t* posA, const int32_t* posB) {
+    const int lim = st.totA < st.totB ? st.totA : st.totB;
+    int c = 0;
+    for (int k = 1 + tid; k <= lim; k += T) c += (posA[k] < posB[k]);
+    return c;
+}
+B2P_HD void bp_swap(const BlockPartState& st, uint64_t* v, int tid, int T, const int32_t* posA, const int32_t* posB) {
+    for (int k = 1 + tid; k <= st.K; k += T) {
+        const uint64_t t = v[posA[k]]; v[posA[k]] = v[posB[k]]; v[posB[k]] = t;
+    }
+}
+B2P_HD long bp_cut(const BlockPartState& st, const int32_t* posA, const int32_t* posB) {
+    const long a_next = (st.K + 1 <= st.totA) ? posA[st.K + 1] : st.last;
+    return (st.K > 0 && posB[st.K] < a_next) ? posB[st.K] : a_next;
+}
+
+#if !defined(__CUDA_ARCH__)
+// host emulation of one block partition with T virtual threads (tests)
+inline long block_partition_host(uint64_t* v, long first, long last, int T, int32_t* posA, int32_t* posB) {
+    BlockPartState st;
+    bp_prepare(st, v, first, last, T);
+    int* cA = new int[T]; int* cB = new int[T];
+    for (int t = 0; t < T; ++t) bp_count(st, v, t, &cA[t], &cB[t]);
+    int totA = 0, totB = 0;
+    for (int t = 0; t < T; ++t) { totA += cA[t]; totB += cB[t]; }
+    st.totA = totA; st.totB = totB;
+    int offA = 0, left = 0;
+    for (int t = 0; t < T; ++t) {
+        bp_scatter(st, v, t, offA, totB - left - cB[t], posA, posB);
+        offA += cA[t]; left += cB[t];
+    }
+    int K = 0;
+    for (int t = 0; t < T; ++t) K += bp_count_swaps(st, t, T, posA, posB);
+    st.K = K;
+    for (int t = 0; t < T; ++t) bp_swap(st, v, t, T, posA, posB);
+    delete[] cA; delete[] cB;
+    return bp_cut(st, posA, posB);
+}
+#endif
+
 // stable insertion sort of a leaf (<= 16 elements) = what __final_insertion_sort does inside one introsort leaf
 B2P_HD void leaf_insertion_sort(uint64_t* v, long first, long last) {
     for (long i = first + 1; i < last; ++i) {
@@ -333,8 +426,10 @@ B2P_HD void leaf_insertion_sort(uint64_t* v, long first, long last) {
 
 #if !defined(__CUDA_ARCH__)
 // host reference driver of the parallel formulation (tests): same partition routine, explicit stack
-inline void par_std_sort_host(uint64_t* v, int n) {
+inline void par_std_sort_host(uint64_t* v, int n, int big = 1 << 30, int T = 512) {
     if (n <= 1) return;
+    int32_t* posA = new int32_t[n + 2];
+    int32_t* posB = new int32_t[n + 2];
     int lg = 0;
     for (int m = n; m > 1; m >>= 1) ++lg;
     long sf[128], sl[128];
@@ -348,13 +443,15 @@ inline void par_std_sort_host(uint64_t* v, int n) {
         while (last - first > 16) {
             if (depth == 0) { seq_heap_sort(v, first, last); heap_sorted = true; break; }
             --depth;
-            const long cut = warp_partition(v, first, last);
+            const long cut = (last - first > big) ? block_partition_host(v, first, last, T, posA, posB)
+                                                  : warp_partition(v, first, last);
             if (last - cut > 16) { sf[sp] = cut; sl[sp] = last; sd[sp] = depth; ++sp; }
             else leaf_insertion_sort(v, cut, last);
             last = cut;
         }
         if (!heap_sorted) leaf_insertion_sort(v, first, last);
     }
+    delete[] posA; delete[] posB;
 }
 #endif
 

@@ -175,12 +175,18 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
 // per-warp local stacks; each warp pops a range, partitions it with warp_partition() (exact emulation of the
 // sequential Hoare loop), publishes the right part for other warps and keeps the left part.  Parts of <= 16 elements
 // are insertion-sorted in place - together that is exactly __introsort_loop + __final_insertion_sort.
-constexpr int kSortQ = 64, kSortLocal = 48, kLimbWarps = kLimbThreads / 32;
+constexpr int kSortQ = 256, kSortLocal = 48, kLimbWarps = kLimbThreads / 32;
+constexpr int kBigRange = 4096, kBigStack = 96;   // ranges above kBigRange are partitioned by the whole block
 struct SortShared {
     int lock, top, pending;
     int sf[kSortQ], sl[kSortQ], sd[kSortQ];
     int ltop[kLimbWarps];
     int lf[kLimbWarps][kSortLocal], ll[kLimbWarps][kSortLocal], ld[kLimbWarps][kSortLocal];
+    // block phase
+    BlockPartState bp;
+    int big_top, kind, cur_f, cur_l, cur_d;
+    int bf[kBigStack], bl[kBigStack], bd[kBigStack];
+    int scan[kLimbThreads / 32 + 1];
 };
 
 // Stable sort of up to two leaves (<= 16 keys each) by one warp: lanes 0-15 take leaf 0, lanes 16-31 leaf 1; every key's
@@ -202,9 +208,9 @@ __device__ __forceinline__ void warp_sort_two_leaves(uint64_t* v, long f0, long 
     __syncwarp();
 }
 
-__device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh) {
+__device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh, int32_t* posA, int32_t* posB) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { sh.lock = 0; sh.top = 0; sh.pending = 0; }
+    if (tid == 0) { sh.lock = 0; sh.top = 0; sh.pending = 0; sh.big_top = 0; }
     if (tid < kLimbWarps) sh.ltop[tid] = 0;
     __syncthreads();
     if (n <= 16) {
@@ -215,9 +221,64 @@ __device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh) {
     if (tid == 0) {
         int lg = 0;
         for (int m = n; m > 1; m >>= 1) ++lg;
-        sh.sf[0] = 0; sh.sl[0] = n; sh.sd[0] = 2 * lg; sh.top = 1; sh.pending = 1;
+        sh.bf[0] = 0; sh.bl[0] = n; sh.bd[0] = 2 * lg; sh.big_top = 1;
     }
     __syncthreads();
+    // ---- phase 1: ranges > kBigRange, one at a time, all threads (rank-based exact partition, post_core.h)
+    for (;;) {
+        if (tid == 0) {
+            if (sh.big_top == 0) sh.kind = 0;
+            else {
+                const int t = --sh.big_top;
+                int f = sh.bf[t], l = sh.bl[t], d = sh.bd[t];
+                if (l - f <= 16) { leaf_insertion_sort(v, f, l); sh.kind = 2; }
+                else if ((l - f <= kBigRange || posA == nullptr) && sh.top < kSortQ) {
+                    const int q = sh.top++;
+                    sh.sf[q] = f; sh.sl[q] = l; sh.sd[q] = d; sh.pending += 1; sh.kind = 2;
+                } else if (d == 0) { seq_heap_sort(v, f, l); sh.kind = 2; }
+                else if (posA == nullptr) {   // no scratch and the warp stack is full: cannot happen for n <= kBigRange
+                    seq_std_sort(v + f, l - f); sh.kind = 2;
+                } else {
+                    sh.cur_f = f; sh.cur_l = l; sh.cur_d = d - 1;
+                    bp_prepare(sh.bp, v, f, l, kLimbThreads);
+                    sh.kind = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int kind = sh.kind;
+        if (kind == 0) break;
+        if (kind == 2) { __syncthreads(); continue; }
+        int cA, cB, totA, totB, K;
+        bp_count(sh.bp, v, tid, &cA, &cB);
+        const int offA = block_exclusive_scan(cA, &totA, sh.scan);
+        const int offBl = block_exclusive_scan(cB, &totB, sh.scan);
+        if (tid == 0) { sh.bp.totA = totA; sh.bp.totB = totB; }
+        __syncthreads();
+        bp_scatter(sh.bp, v, tid, offA, totB - offBl - cB, posA, posB);
+        __syncthreads();
+        block_exclusive_scan(bp_count_swaps(sh.bp, tid, kLimbThreads, posA, posB), &K, sh.scan);
+        if (tid == 0) sh.bp.K = K;
+        __syncthreads();
+        bp_swap(sh.bp, v, tid, kLimbThreads, posA, posB);
+        __syncthreads();
+        if (tid == 0) {
+            const int cut = (int)bp_cut(sh.bp, posA, posB);
+            int t = sh.big_top;
+            if (t + 2 <= kBigStack) {
+                sh.bf[t] = sh.cur_f; sh.bl[t] = cut; sh.bd[t] = sh.cur_d; ++t;
+                sh.bf[t] = cut; sh.bl[t] = sh.cur_l; sh.bd[t] = sh.cur_d; ++t;
+                sh.big_top = t;
+            } else {   // unreachable (depth <= 2 log2 n), keep exactness anyway
+                seq_std_sort(v + sh.cur_f, cut - sh.cur_f);
+                seq_std_sort(v + cut, sh.cur_l - cut);
+            }
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- phase 2: ranges <= kBigRange on the shared stack, one warp per range (chunked exact partition)
     unsigned idle = 0;
     for (;;) {
         int f = 0, l = 0, d = 0, state = 0;    // state: 0 nothing yet, 1 got a range, 2 all done
@@ -364,6 +425,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     const int per = (npairs + kLimbThreads - 1) / kLimbThreads;
     const int p_begin = min(npairs, tid * per), p_end = min(npairs, p_begin + per);
 
+    const long long t_start = clock64();
     // pass 1: count the candidates of this thread's contiguous slice of (a, b) pairs
     int cnt = 0;
     for (int p = p_begin; p < p_end; ++p) {
@@ -378,10 +440,13 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
         return;
     }
     unsigned long long* keys = sm_keys;
+    int32_t *posA = nullptr, *posB = nullptr;
     if (n > pb.cand_smem_cap) {
-        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, (unsigned long long)n);
+        // n keys + (n + 2) entries of rank->position scratch for the block-level partition
+        const unsigned long long need = 2ull * n + 2;
+        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, need);
         __syncthreads();
-        if (s_pool_base + n > pb.pool_cap) {
+        if (s_pool_base + (long)need > pb.pool_cap) {
             if (tid == 0) {
                 atomicOr(&pb.status[img], 2);
                 *out_cnt = 0;
@@ -389,6 +454,8 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
             return;
         }
         keys = pb.pool + s_pool_base;
+        posA = reinterpret_cast<int32_t*>(keys + n);
+        posB = posA + n + 2;
     }
     // pass 2: keys in generation order (a-major, b-minor) = the order the reference pushes candidates in
     for (int p = p_begin; p < p_end; ++p) {
@@ -399,12 +466,23 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     for (int i = tid; i < 64; i += kLimbThreads) { used_a[i] = 0; used_b[i] = 0; }
     __threadfence();
     __syncthreads();
-    block_exact_sort(reinterpret_cast<uint64_t*>(keys), n, s_sort);     // std::sort, pafprocess.cpp:97
+    const long long t_scored = clock64();
+    block_exact_sort(reinterpret_cast<uint64_t*>(keys), n, s_sort, posA, posB);     // std::sort, pafprocess.cpp:97
+    const long long t_sorted = clock64();
     if (tid < 32) {
         const long o = ((long)img * kNumLimb + limb) * cap;
         const int nc = greedy_match_warp(reinterpret_cast<const uint64_t*>(keys), n, nb, used_a, used_b, min(na, nb),
                                          pb.conn_a + o, pb.conn_b + o, pb.conn_s + o);
-        if (tid == 0) *out_cnt = nc;
+        if (tid == 0) {
+            *out_cnt = nc;
+            if (pb.dbg) {   // phase maxima over blocks (cycles): scoring+compaction, sort, greedy; and max candidates
+                atomicMax(pb.dbg + 0, (unsigned long long)(t_scored - t_start));
+                atomicMax(pb.dbg + 1, (unsigned long long)(t_sorted - t_scored));
+                atomicMax(pb.dbg + 2, (unsigned long long)(clock64() - t_sorted));
+                atomicMax(pb.dbg + 3, (unsigned long long)n);
+                atomicAdd(pb.dbg + 4, (unsigned long long)n);
+            }
+        }
     }
 }
 
@@ -556,6 +634,8 @@ cudaError_t post_alloc(PostBuffers& pb, int batch_cap, int peak_cap, int human_c
     B2P_TRY(cudaMalloc(&pb.n_humans, B * sizeof(int)));
     B2P_TRY(cudaMalloc(&pb.humans, B * human_cap * kHumanFloats * sizeof(float)));
     B2P_TRY(cudaMalloc(&pb.status, B * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.dbg, 16 * sizeof(unsigned long long)));
+    B2P_TRY(cudaMemset(pb.dbg, 0, 16 * sizeof(unsigned long long)));
     B2P_TRY(cudaMemset(pb.status, 0, B * sizeof(int)));
     B2P_TRY(cudaMemset(pb.counts, 0, B * kNumPart * sizeof(int)));
     return cudaSuccess;
@@ -564,7 +644,7 @@ cudaError_t post_alloc(PostBuffers& pb, int batch_cap, int peak_cap, int human_c
 void post_free(PostBuffers& pb) {
     void* ptrs[] = {pb.counts, pb.peak_x, pb.peak_y, pb.peak_s,  pb.conn_cnt, pb.conn_a,      pb.conn_b,
                     pb.conn_s, pb.rows,   pb.alive,  pb.lists,   pb.list_n,   pb.id_score,    pb.id_xy,
-                    pb.pool,   pb.pool_cursor, pb.n_humans, pb.humans, pb.status};
+                    pb.pool,   pb.pool_cursor, pb.n_humans, pb.humans, pb.status, pb.dbg};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     memset(&pb, 0, sizeof(pb));

@@ -38,6 +38,7 @@ struct PostBuffers {
     // results
     int* n_humans;      // [B]
     float* humans;      // [B][human_cap][1 + 18*4]: score, then per part (x, y, peak score, cid or -1)
+    unsigned long long* dbg;   // [16] diagnostics: max cycles per limbs_kernel phase, candidate counts
     int* status;        // [B] bit0 peak overflow, bit1 candidate pool overflow, bit2 row overflow, bit3 human overflow,
                         //     bit4 assembler used the slow scan, bit8.. number of limbs that needed the tie-exact sort
 };

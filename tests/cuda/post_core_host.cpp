@@ -109,9 +109,11 @@ extern "C" int core_ties() { return g_ties; }
 extern "C" int core_sort_mismatch() { return g_sort_mismatch; }
 // direct test hook: sort `n` keys with both formulations, return 0 when identical
 extern "C" int core_sort_check(uint64_t* keys, int n, uint64_t* out) {
-    std::vector<uint64_t> seq(keys, keys + n), par(keys, keys + n);
+    std::vector<uint64_t> seq(keys, keys + n), par(keys, keys + n), blk(keys, keys + n), blk2(keys, keys + n);
     seq_std_sort(seq.data(), n);
-    par_std_sort_host(par.data(), n);
+    par_std_sort_host(par.data(), n);                 // warp-chunked partition everywhere
+    par_std_sort_host(blk.data(), n, 64, 7);          // rank-based block partition for ranges > 64, 7 virtual threads
+    par_std_sort_host(blk2.data(), n, 300, 512);      // ... > 300 with 512 virtual threads (mostly empty slices)
     for (int i = 0; i < n; ++i) out[i] = par[i];
-    return seq == par ? 0 : 1;
+    return (seq == par ? 0 : 1) | (seq == blk ? 0 : 2) | (seq == blk2 ? 0 : 4);
 }
