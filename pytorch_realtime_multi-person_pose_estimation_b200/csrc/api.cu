@@ -507,8 +507,9 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
     CU(cudaSetDevice(cuda_device));
     b200pose_post* p = new b200pose_post();
     p->device = cuda_device;
-    // candidate-key pool: 1 Mi keys (8 MB) per image of the batch, capped at 1 GiB; exhausting it sets a status bit
-    const long pool = (long)batch_cap * (1L << 20) < (1L << 27) ? (long)batch_cap * (1L << 20) : (1L << 27);
+    // candidate-key pool: 6 Mi entries (48 MB) per image of the batch (capped at 2 GiB) - key slots for every (a, b) pair of the limbs that do not
+    // fit shared memory plus partition scratch, i.e. ~2 M pairs per image - capped at 1 GiB; exhausting it sets a status bit (loud error in the Python layer)
+    const long pool = (long)batch_cap * (6L << 20) < (1L << 28) ? (long)batch_cap * (6L << 20) : (1L << 28);
     cudaError_t e = post_alloc(p->pb, batch_cap, peak_cap, human_cap, pool);
     if (e != cudaSuccess) { delete p; return fail("post_alloc failed: %s", cudaGetErrorString(e)); }
     CU(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));

@@ -51,6 +51,12 @@ struct PafView {
     B2P_HD float at(int c, int y, int x) const { return base[c * sc + (long)(y >> shift) * sy + (long)(x >> shift) * sx]; }
 };
 
+// roundpaf (pafprocess.cpp:240-242) is `(int)(v + 0.5)` evaluated in DOUBLE.  For 0 <= v <= 16384 the single-precision
+// form gives the same integer for every float except v = 0x1.fffffep-2 (largest float below 0.5, where v + 0.5f rounds
+// up to 1.0f) - checked exhaustively over all 1.18e9 floats of that range - so one compare keeps it exact while avoiding
+// the FP64 conversion pipe (20 conversions per candidate pair).
+B2P_HD int round_half_up(float v) { return v == 0x1.fffffep-2f ? 0 : (int)f_add(v, 0.5f); }
+
 // Scores one (a, b) peak pair of a limb.  Returns true and the candidate score if it passes both criteria.
 B2P_HD bool pair_score(const PafView& paf, int c1, int c2, int ax, int ay, int bx, int by, int h_up, float* score_out) {
     const int dxi = bx - ax, dyi = by - ay;
@@ -64,8 +70,8 @@ B2P_HD bool pair_score(const PafView& paf, int c1, int c2, int ax, int ay, int b
     float scores = 0.0f;
     int crit1 = 0;
     for (int i = 0; i < kStepPaf; ++i) {
-        const int lx = (int)((double)f_add((float)ax, f_mul((float)i, step_x)) + 0.5);
-        const int ly = (int)((double)f_add((float)ay, f_mul((float)i, step_y)) + 0.5);
+        const int lx = round_half_up(f_add((float)ax, f_mul((float)i, step_x)));
+        const int ly = round_half_up(f_add((float)ay, f_mul((float)i, step_y)));
         const float s = f_add(f_mul(vx, paf.at(c1, ly, lx)), f_mul(vy, paf.at(c2, ly, lx)));
         scores = f_add(scores, s);
         if (s > 0.05f) crit1 += 1;
@@ -253,7 +259,8 @@ B2P_HD uint32_t chunk_mask_hi(const uint64_t* v, long c, long first, uint32_t pi
 #endif
 }
 
-B2P_HD long warp_partition(uint64_t* v, long first, long last) {
+// wscr: 64 bytes of per-warp shared scratch on the device (rank -> lane tables); unused on the host.
+B2P_HD long warp_partition(uint64_t* v, long first, long last, unsigned char* wscr = nullptr) {
     if (B2P_LANE() == 0) {   // __move_median_to_first(first, first+1, mid, last-1)
         const long a = first + 1, b = first + (last - first) / 2, c = last - 1;
         long m;
@@ -281,15 +288,24 @@ B2P_HD long warp_partition(uint64_t* v, long first, long last) {
         long lo_k = 0, hi_k = 0; // of pair kp (the first failing one) or garbage if kp == m
         long last_lo = 0, last_hi = 0;
 #if defined(__CUDA_ARCH__)
+        int ja_last, jb_last;    // bit positions of the m-th stops
         {
+            // k-th set bit of each mask for lane k: the lane sitting on a set bit knows its rank (popc below it) and
+            // publishes its index at table[rank]  (__fns would cost ~100 instructions per call)
             const int k = B2P_LANE();
+            const uint32_t below = (1u << k) - 1u;
+            if ((effA >> k) & 1u) wscr[__popc(effA & below)] = (unsigned char)k;
+            if ((effB >> k) & 1u) wscr[32 + __popc(effB & below)] = (unsigned char)k;
+            __syncwarp();
             long mylo = 0, myhi = 0;
             bool ok = false;
             if (k < m) {
-                mylo = cA + nth_set_bit(effA, k);
-                myhi = cB - 1 - nth_set_bit(effB, k);
+                mylo = cA + wscr[k];
+                myhi = cB - 1 - wscr[32 + k];
                 ok = mylo < myhi;
             }
+            ja_last = wscr[m - 1];
+            jb_last = wscr[32 + m - 1];
             const uint32_t okm = __ballot_sync(0xffffffffu, ok);
             kp = __popc(okm);     // ok is monotone in k: lo_k increases, hi_k decreases
             if (ok) { const uint64_t t = v[mylo]; v[mylo] = v[myhi]; v[myhi] = t; }
@@ -316,8 +332,13 @@ B2P_HD long warp_partition(uint64_t* v, long first, long last) {
             return (kp > 0 && last_hi < lo_k) ? last_hi : lo_k;
         }
         // all m pairs swapped: the scans have passed the consumed stops
+#if defined(__CUDA_ARCH__)
+        rawA &= ~low_bits(ja_last + 1);
+        rawB &= ~low_bits(jb_last + 1);
+#else
         rawA &= ~low_bits(nth_set_bit(effA, m - 1) + 1);
         rawB &= ~low_bits(nth_set_bit(effB, m - 1) + 1);
+#endif
     }
 }
 
@@ -355,7 +376,14 @@ B2P_HD void bp_count(const BlockPartState& st, const uint64_t* v, int tid, int* 
     long s, e;
     bp_slice(st, tid, &s, &e);
     int a = 0, b = 0;
-    for (long p = s; p < e; ++p) {
+    long p = s;
+    for (; p + 4 <= e; p += 4) {     // four independent loads in flight (the slices live in L2 / HBM)
+        const uint32_t k0 = (uint32_t)(v[p] >> 32), k1 = (uint32_t)(v[p + 1] >> 32);
+        const uint32_t k2 = (uint32_t)(v[p + 2] >> 32), k3 = (uint32_t)(v[p + 3] >> 32);
+        a += (k0 >= st.pivot) + (k1 >= st.pivot) + (k2 >= st.pivot) + (k3 >= st.pivot);
+        b += (k0 <= st.pivot) + (k1 <= st.pivot) + (k2 <= st.pivot) + (k3 <= st.pivot);
+    }
+    for (; p < e; ++p) {
         const uint32_t k = (uint32_t)(v[p] >> 32);
         a += (k >= st.pivot);
         b += (k <= st.pivot);
@@ -368,10 +396,28 @@ B2P_HD void bp_scatter(const BlockPartState& st, const uint64_t* v, int tid, int
     long s, e;
     bp_slice(st, tid, &s, &e);
     int a = offA;
-    for (long p = s; p < e; ++p)
+    long p = s;
+    for (; p + 4 <= e; p += 4) {
+        const uint32_t k0 = (uint32_t)(v[p] >> 32), k1 = (uint32_t)(v[p + 1] >> 32);
+        const uint32_t k2 = (uint32_t)(v[p + 2] >> 32), k3 = (uint32_t)(v[p + 3] >> 32);
+        if (k0 >= st.pivot) posA[++a] = (int32_t)p;
+        if (k1 >= st.pivot) posA[++a] = (int32_t)(p + 1);
+        if (k2 >= st.pivot) posA[++a] = (int32_t)(p + 2);
+        if (k3 >= st.pivot) posA[++a] = (int32_t)(p + 3);
+    }
+    for (; p < e; ++p)
         if ((uint32_t)(v[p] >> 32) >= st.pivot) posA[++a] = (int32_t)p;
     int b = b_right;
-    for (long p = e - 1; p >= s; --p)
+    p = e - 1;
+    for (; p - 3 >= s; p -= 4) {
+        const uint32_t k0 = (uint32_t)(v[p] >> 32), k1 = (uint32_t)(v[p - 1] >> 32);
+        const uint32_t k2 = (uint32_t)(v[p - 2] >> 32), k3 = (uint32_t)(v[p - 3] >> 32);
+        if (k0 <= st.pivot) posB[++b] = (int32_t)p;
+        if (k1 <= st.pivot) posB[++b] = (int32_t)(p - 1);
+        if (k2 <= st.pivot) posB[++b] = (int32_t)(p - 2);
+        if (k3 <= st.pivot) posB[++b] = (int32_t)(p - 3);
+    }
+    for (; p >= s; --p)
         if ((uint32_t)(v[p] >> 32) <= st.pivot) posB[++b] = (int32_t)p;
 }
 B2P_HD int bp_count_swaps(const BlockPartState& st, int tid, int T, const int32_t* posA, const int32_t* posB) {

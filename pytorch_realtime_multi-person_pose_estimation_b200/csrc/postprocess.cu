@@ -171,22 +171,29 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
     return res;
 }
 
-// Exact std::sort (libstdc++ introsort) of `n` keys by the whole block: ranges live on a small shared stack plus
-// per-warp local stacks; each warp pops a range, partitions it with warp_partition() (exact emulation of the
-// sequential Hoare loop), publishes the right part for other warps and keeps the left part.  Parts of <= 16 elements
-// are insertion-sorted in place - together that is exactly __introsort_loop + __final_insertion_sort.
-constexpr int kSortQ = 256, kSortLocal = 48, kLimbWarps = kLimbThreads / 32;
-constexpr int kBigRange = 4096, kBigStack = 96;   // ranges above kBigRange are partitioned by the whole block
+// Exact std::sort (libstdc++ introsort) of `n` keys by the whole block, hierarchical:
+//   level G (keys in global memory, n > kSmemRange): ranges are partitioned one at a time by all threads with the
+//            rank-based exact partition (post_core.h bp_*), scratch (rank -> position) in global memory;
+//   level S: every range of <= kSmemRange keys is copied into shared memory and sorted there completely -
+//            block-level partitions down to <= kWarpRange keys, then a work queue of ranges, one warp per range with
+//            the chunked exact partition (warp_partition), parts of <= 16 keys by a rank-based stable leaf sort -
+//            and copied back.
+// Together this is exactly __introsort_loop + __final_insertion_sort, including the order of equal keys.
+constexpr int kSortQ = 128, kSortLocal = 40, kLimbWarps = kLimbThreads / 32;
+constexpr int kSmemRange = 4096, kWarpRange = 512, kBigStack = 80;
 struct SortShared {
     int lock, top, pending;
     int sf[kSortQ], sl[kSortQ], sd[kSortQ];
     int ltop[kLimbWarps];
     int lf[kLimbWarps][kSortLocal], ll[kLimbWarps][kSortLocal], ld[kLimbWarps][kSortLocal];
-    // block phase
     BlockPartState bp;
-    int big_top, kind, cur_f, cur_l, cur_d;
-    int bf[kBigStack], bl[kBigStack], bd[kBigStack];
+    int kind, cur_f, cur_l, cur_d;
+    int s_top, s_f[kBigStack], s_l[kBigStack], s_d[kBigStack];    // level S block-phase stack
+    int g_top, g_f[kBigStack], g_l[kBigStack], g_d[kBigStack];    // level G stack
     int scan[kLimbThreads / 32 + 1];
+    unsigned long long scan2[kLimbThreads / 32 + 1];
+    int ksum;
+    unsigned char wscr[kLimbWarps][64];     // rank -> lane tables of warp_partition
 };
 
 // Stable sort of up to two leaves (<= 16 keys each) by one warp: lanes 0-15 take leaf 0, lanes 16-31 leaf 1; every key's
@@ -208,89 +215,148 @@ __device__ __forceinline__ void warp_sort_two_leaves(uint64_t* v, long f0, long 
     __syncwarp();
 }
 
-__device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh, int32_t* posA, int32_t* posB) {
+// Exclusive scan of two counters at once (packed in one 64-bit word, counts < 2^31) + their totals.
+__device__ __forceinline__ void block_exclusive_scan2(int a, int b, int* offA, int* offB, int* totA, int* totB,
+                                                      unsigned long long* scratch /*[warps + 1]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned long long v = ((unsigned long long)(unsigned)b << 32) | (unsigned)a;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    unsigned long long pre = 0, tot = 0;
+    for (int k = 0; k < nw; ++k) {
+        const unsigned long long c = scratch[k];
+        if (k < warp) pre += c;
+        tot += c;
+    }
+    const unsigned long long ex = pre + inc - v;
+    *offA = (int)(unsigned)ex; *offB = (int)(ex >> 32);
+    *totA = (int)(unsigned)tot; *totB = (int)(tot >> 32);
+    __syncthreads();
+}
+
+// One exact block-level partition of v[f, l) (all threads).  Returns the cut (uniform).
+__device__ int block_partition(uint64_t* v, int f, int l, SortShared& sh, int32_t* posA, int32_t* posB) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { bp_prepare(sh.bp, v, f, l, kLimbThreads); sh.ksum = 0; }
+    __syncthreads();
+    int cA, cB, offA, offBl, totA, totB;
+    bp_count(sh.bp, v, tid, &cA, &cB);
+    block_exclusive_scan2(cA, cB, &offA, &offBl, &totA, &totB, sh.scan2);
+    BlockPartState st = sh.bp;
+    st.totA = totA; st.totB = totB;
+    bp_scatter(st, v, tid, offA, totB - offBl - cB, posA, posB);
+    __syncthreads();
+    int c = bp_count_swaps(st, tid, kLimbThreads, posA, posB);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0 && c) atomicAdd(&sh.ksum, c);
+    __syncthreads();
+    st.K = sh.ksum;
+    bp_swap(st, v, tid, kLimbThreads, posA, posB);
+    __syncthreads();
+    return (int)bp_cut(st, posA, posB);
+}
+
+// Left-descending introsort loop of one warp on v[f, l): partitions, hands the right parts to the shared stack (or its
+// own local stack), leaf-sorts parts of <= 16 keys.
+__device__ void warp_descend(uint64_t* v, int f, int l, int d, SortShared& sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool heap_sorted = false;
+    while (l - f > 16) {
+        if (d == 0) {                      // depth limit exhausted: std::__partial_sort == heap sort
+            if (lane == 0) seq_heap_sort(v, f, l);
+            __syncwarp();
+            heap_sorted = true;
+            break;
+        }
+        --d;
+        const int cut = (int)warp_partition(v, f, l, sh.wscr[warp]);
+        if (l - cut > 16) {
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&sh.pending, 1);
+                bool pushed = false;
+                while (atomicCAS(&sh.lock, 0, 1) != 0) {}
+                if (sh.top < kSortQ) { const int t = sh.top++; sh.sf[t] = cut; sh.sl[t] = l; sh.sd[t] = d; pushed = true; }
+                __threadfence_block();
+                atomicExch(&sh.lock, 0);
+                if (!pushed) {
+                    const int t = sh.ltop[warp];
+                    if (t < kSortLocal) { sh.lf[warp][t] = cut; sh.ll[warp][t] = l; sh.ld[warp][t] = d; sh.ltop[warp] = t + 1; }
+                    else { seq_std_sort(v + cut, l - cut); atomicSub(&sh.pending, 1); }   // unreachable (depth bound)
+                }
+            }
+        } else {
+            warp_sort_two_leaves(v, cut, l, 0, 0);
+        }
+        l = cut;
+        __syncwarp();
+    }
+    if (!heap_sorted) warp_sort_two_leaves(v, f, l, 0, 0);
+    __syncwarp();
+}
+
+// Level S: complete exact sort of w[f, l) (w = shared-memory resident keys, indices as given) with depth budget d.
+// scrA/scrB: rank->position scratch for block partitions (may be null when l - f <= kWarpRange is guaranteed... it is
+// only dereferenced for ranges > kWarpRange).
+__device__ void smem_sort_range(uint64_t* w, int f, int l, int d, SortShared& sh, int32_t* scrA, int32_t* scrB,
+                                unsigned long long* dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { sh.lock = 0; sh.top = 0; sh.pending = 0; sh.big_top = 0; }
+    const long long t0 = clock64();
+    if (tid == 0) { sh.lock = 0; sh.top = 0; sh.pending = 0; sh.s_top = 1; sh.s_f[0] = f; sh.s_l[0] = l; sh.s_d[0] = d; }
     if (tid < kLimbWarps) sh.ltop[tid] = 0;
     __syncthreads();
-    if (n <= 16) {
-        if (tid == 0) leaf_insertion_sort(v, 0, n);
-        __syncthreads();
-        return;
-    }
-    if (tid == 0) {
-        int lg = 0;
-        for (int m = n; m > 1; m >>= 1) ++lg;
-        sh.bf[0] = 0; sh.bl[0] = n; sh.bd[0] = 2 * lg; sh.big_top = 1;
-    }
-    __syncthreads();
-    // ---- phase 1: ranges > kBigRange, one at a time, all threads (rank-based exact partition, post_core.h)
+    // block phase: ranges > kWarpRange
     for (;;) {
         if (tid == 0) {
-            if (sh.big_top == 0) sh.kind = 0;
+            if (sh.s_top == 0) sh.kind = 0;
             else {
-                const int t = --sh.big_top;
-                int f = sh.bf[t], l = sh.bl[t], d = sh.bd[t];
-                if (l - f <= 16) { leaf_insertion_sort(v, f, l); sh.kind = 2; }
-                else if ((l - f <= kBigRange || posA == nullptr) && sh.top < kSortQ) {
+                const int t = --sh.s_top;
+                const int rf = sh.s_f[t], rl = sh.s_l[t], rd = sh.s_d[t];
+                if (rl - rf <= 16) { leaf_insertion_sort(w, rf, rl); sh.kind = 2; }
+                else if ((rl - rf <= kWarpRange || scrA == nullptr) && sh.top < kSortQ) {
                     const int q = sh.top++;
-                    sh.sf[q] = f; sh.sl[q] = l; sh.sd[q] = d; sh.pending += 1; sh.kind = 2;
-                } else if (d == 0) { seq_heap_sort(v, f, l); sh.kind = 2; }
-                else if (posA == nullptr) {   // no scratch and the warp stack is full: cannot happen for n <= kBigRange
-                    seq_std_sort(v + f, l - f); sh.kind = 2;
-                } else {
-                    sh.cur_f = f; sh.cur_l = l; sh.cur_d = d - 1;
-                    bp_prepare(sh.bp, v, f, l, kLimbThreads);
-                    sh.kind = 1;
-                }
+                    sh.sf[q] = rf; sh.sl[q] = rl; sh.sd[q] = rd; sh.pending += 1; sh.kind = 2;
+                } else if (rd == 0) { seq_heap_sort(w, rf, rl); sh.kind = 2; }
+                else if (scrA == nullptr) { seq_std_sort(w + rf, rl - rf); sh.kind = 2; }
+                else { sh.cur_f = rf; sh.cur_l = rl; sh.cur_d = rd - 1; sh.kind = 1; }
             }
         }
         __syncthreads();
         const int kind = sh.kind;
         if (kind == 0) break;
         if (kind == 2) { __syncthreads(); continue; }
-        int cA, cB, totA, totB, K;
-        bp_count(sh.bp, v, tid, &cA, &cB);
-        const int offA = block_exclusive_scan(cA, &totA, sh.scan);
-        const int offBl = block_exclusive_scan(cB, &totB, sh.scan);
-        if (tid == 0) { sh.bp.totA = totA; sh.bp.totB = totB; }
-        __syncthreads();
-        bp_scatter(sh.bp, v, tid, offA, totB - offBl - cB, posA, posB);
-        __syncthreads();
-        block_exclusive_scan(bp_count_swaps(sh.bp, tid, kLimbThreads, posA, posB), &K, sh.scan);
-        if (tid == 0) sh.bp.K = K;
-        __syncthreads();
-        bp_swap(sh.bp, v, tid, kLimbThreads, posA, posB);
-        __syncthreads();
+        const int cf = sh.cur_f, cl = sh.cur_l, cd = sh.cur_d;
+        const int cut = block_partition(w, cf, cl, sh, scrA, scrB);
         if (tid == 0) {
-            const int cut = (int)bp_cut(sh.bp, posA, posB);
-            int t = sh.big_top;
-            if (t + 2 <= kBigStack) {
-                sh.bf[t] = sh.cur_f; sh.bl[t] = cut; sh.bd[t] = sh.cur_d; ++t;
-                sh.bf[t] = cut; sh.bl[t] = sh.cur_l; sh.bd[t] = sh.cur_d; ++t;
-                sh.big_top = t;
-            } else {   // unreachable (depth <= 2 log2 n), keep exactness anyway
-                seq_std_sort(v + sh.cur_f, cut - sh.cur_f);
-                seq_std_sort(v + cut, sh.cur_l - cut);
-            }
+            int t = sh.s_top;
+            sh.s_f[t] = cf; sh.s_l[t] = cut; sh.s_d[t] = cd; ++t;
+            sh.s_f[t] = cut; sh.s_l[t] = cl; sh.s_d[t] = cd; ++t;
+            sh.s_top = t;      // depth-first: <= 2 + depth entries, depth <= 2 log2(n) - log2(n / kSmemRange) ...
         }
         __syncthreads();
     }
-    __threadfence();
     __syncthreads();
-    // ---- phase 2: ranges <= kBigRange on the shared stack, one warp per range (chunked exact partition)
+    const long long t1 = clock64();
+    // warp phase: work queue
     unsigned idle = 0;
     for (;;) {
-        int f = 0, l = 0, d = 0, state = 0;    // state: 0 nothing yet, 1 got a range, 2 all done
+        int rf = 0, rl = 0, rd = 0, state = 0;    // state: 0 nothing yet, 1 got a range, 2 all done
         if (lane == 0) {
             if (sh.ltop[warp] > 0) {
                 const int t = --sh.ltop[warp];
-                f = sh.lf[warp][t]; l = sh.ll[warp][t]; d = sh.ld[warp][t]; state = 1;
+                rf = sh.lf[warp][t]; rl = sh.ll[warp][t]; rd = sh.ld[warp][t]; state = 1;
             } else {
                 while (atomicCAS(&sh.lock, 0, 1) != 0) {}
                 if (sh.top > 0) {
                     const int t = --sh.top;
-                    f = sh.sf[t]; l = sh.sl[t]; d = sh.sd[t]; state = 1;
+                    rf = sh.sf[t]; rl = sh.sl[t]; rd = sh.sd[t]; state = 1;
                 }
                 __threadfence_block();
                 atomicExch(&sh.lock, 0);
@@ -301,48 +367,66 @@ __device__ void block_exact_sort(uint64_t* v, int n, SortShared& sh, int32_t* po
         if (state == 2) break;
         if (state == 0) {
             if (++idle > (1u << 24)) { printf("[b200pose] exact sort: idle watchdog (block %d,%d)\n", (int)blockIdx.x, (int)blockIdx.y); __trap(); }
-            __nanosleep(200);
+            __nanosleep(100);
             continue;
         }
         idle = 0;
-        f = __shfl_sync(0xffffffffu, f, 0);
-        l = __shfl_sync(0xffffffffu, l, 0);
-        d = __shfl_sync(0xffffffffu, d, 0);
-        __threadfence();                       // see the swaps of the warp that published this range
-        bool heap_sorted = false;
-        while (l - f > 16) {
-            if (d == 0) {                      // depth limit exhausted: std::__partial_sort == heap sort
-                if (lane == 0) seq_heap_sort(v, f, l);
-                __syncwarp();
-                heap_sorted = true;
-                break;
+        rf = __shfl_sync(0xffffffffu, rf, 0);
+        rl = __shfl_sync(0xffffffffu, rl, 0);
+        rd = __shfl_sync(0xffffffffu, rd, 0);
+        __threadfence_block();                 // see the swaps of the warp that published this range
+        warp_descend(w, rf, rl, rd, sh);
+        if (lane == 0) { __threadfence_block(); atomicSub(&sh.pending, 1); }
+    }
+    __syncthreads();
+    if (dbg && tid == 0) { atomicAdd(dbg + 6, (unsigned long long)(t1 - t0)); atomicAdd(dbg + 7, (unsigned long long)(clock64() - t1)); }
+}
+
+// keys: n keys in generation order, either already in shared memory (n <= kSmemRange: smem_keys == keys) or in global
+// memory with `gA/gB` scratch of n + 2 entries each.  smem_keys / smem_scr: shared buffers of kSmemRange keys and
+// 2 x (kSmemRange + 2) ints.
+__device__ void block_exact_sort(uint64_t* keys, int n, SortShared& sh, uint64_t* smem_keys, int32_t* smem_scr,
+                                 int32_t* gA, int32_t* gB, unsigned long long* dbg) {
+    const int tid = threadIdx.x;
+    if (n <= 1) return;
+    int lg = 0;
+    for (int m = n; m > 1; m >>= 1) ++lg;
+    int32_t* sA = smem_scr;
+    int32_t* sB = smem_scr + kSmemRange + 2;
+    if (keys == smem_keys) {
+        smem_sort_range(keys, 0, n, 2 * lg, sh, sA, sB, nullptr);
+        return;
+    }
+    if (tid == 0) { sh.g_top = 1; sh.g_f[0] = 0; sh.g_l[0] = n; sh.g_d[0] = 2 * lg; }
+    __syncthreads();
+    for (;;) {
+        __syncthreads();
+        if (sh.g_top == 0) break;
+        const int t = sh.g_top - 1;
+        const int f = sh.g_f[t], l = sh.g_l[t], d = sh.g_d[t];
+        __syncthreads();
+        if (tid == 0) sh.g_top = t;
+        if (l - f <= kSmemRange) {
+            // level S: copy in, sort completely in shared memory, copy out
+            for (int i = tid; i < l - f; i += kLimbThreads) smem_keys[i] = keys[f + i];
+            __syncthreads();
+            smem_sort_range(smem_keys - f, f, l, d, sh, sA, sB, dbg);
+            for (int i = tid; i < l - f; i += kLimbThreads) keys[f + i] = smem_keys[i];
+            __syncthreads();
+        } else if (d == 0) {
+            if (tid == 0) seq_heap_sort(keys, f, l);
+            __syncthreads();
+        } else {
+            const long long tg = clock64();
+            const int cut = block_partition(keys, f, l, sh, gA, gB);
+            if (dbg && tid == 0) { atomicAdd(dbg + 5, (unsigned long long)(clock64() - tg)); atomicAdd(dbg + 8, 1ull); }
+            if (tid == 0) {
+                int q = sh.g_top;
+                sh.g_f[q] = f; sh.g_l[q] = cut; sh.g_d[q] = d - 1; ++q;
+                sh.g_f[q] = cut; sh.g_l[q] = l; sh.g_d[q] = d - 1; ++q;
+                sh.g_top = q;
             }
-            --d;
-            const int cut = (int)warp_partition(v, f, l);
-            if (l - cut > 16) {
-                if (lane == 0) {
-                    __threadfence();
-                    atomicAdd(&sh.pending, 1);
-                    bool pushed = false;
-                    while (atomicCAS(&sh.lock, 0, 1) != 0) {}
-                    if (sh.top < kSortQ) { const int t = sh.top++; sh.sf[t] = cut; sh.sl[t] = l; sh.sd[t] = d; pushed = true; }
-                    __threadfence_block();
-                    atomicExch(&sh.lock, 0);
-                    if (!pushed) {
-                        const int t = sh.ltop[warp]++;     // depth <= 2*log2(n) <= 2*31 > kSortLocal only for absurd n
-                        if (t < kSortLocal) { sh.lf[warp][t] = cut; sh.ll[warp][t] = l; sh.ld[warp][t] = d; }
-                        else { sh.ltop[warp] = kSortLocal; atomicSub(&sh.pending, 1); }   // unreachable for n < 2^24
-                    }
-                }
-            } else {
-                warp_sort_two_leaves(v, cut, l, 0, 0);
-            }
-            l = cut;
-            __syncwarp();
         }
-        if (!heap_sorted) warp_sort_two_leaves(v, f, l, 0, 0);
-        __syncwarp();
-        if (lane == 0) { __threadfence(); atomicSub(&sh.pending, 1); }
     }
     __syncthreads();
 }
@@ -353,13 +437,14 @@ __device__ int greedy_match_warp(const uint64_t* keys, int n, int nb, uint32_t* 
                                  int* conn_a, int* conn_b, float* conn_s) {
     const int lane = threadIdx.x & 31;
     int nc = 0;
+    uint64_t k_next = lane < n ? keys[lane] : 0;           // software pipelining: chunk i+1 is in flight while i is matched
     for (int base = 0; base < n && nc < max_conn; base += 32) {
         const int i = base + lane;
-        uint64_t k = 0;
+        const uint64_t k = k_next;
+        if (i + 32 < n) k_next = keys[i + 32];
         int a = -1, b = -1;
         bool free_ = false;
         if (i < n) {
-            k = keys[i];
             const uint32_t pair = (uint32_t)k;
             a = pair / nb;
             b = pair - a * nb;
@@ -386,7 +471,9 @@ __device__ int greedy_match_warp(const uint64_t* keys, int n, int nb, uint32_t* 
 
 __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up, int lw,
                                                              int lh, int paf_in_smem) {
-    extern __shared__ unsigned long long sm_keys[];       // [cand_smem_cap] keys, then (optionally) 2 PAF planes
+    // dynamic smem: [kSmemRange keys][2 x (kSmemRange + 2) int32 partition scratch][optional 2 PAF planes]
+    extern __shared__ unsigned long long sm_keys[];
+    int32_t* sm_scr = reinterpret_cast<int32_t*>(sm_keys + kSmemRange);
     __shared__ uint32_t used_a[64], used_b[64];            // peak_cap <= 2048
     __shared__ int scan_scratch[kLimbThreads / 32 + 1];
     __shared__ long s_pool_base;
@@ -410,7 +497,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     if (paf_in_smem) {
         // the 10 x na x nb line-integral samples of this limb hit only its two PAF planes (2 x h x w floats):
         // stage them in shared memory once instead of gathering from L2 ~1e6 times
-        float* planes = reinterpret_cast<float*>(sm_keys + pb.cand_smem_cap);
+        float* planes = reinterpret_cast<float*>(sm_scr + 2 * (kSmemRange + 2));
         const int hw = lw * lh;
         for (int i = tid; i < 2 * hw; i += kLimbThreads) {
             const int ch = i >= hw, r = i - ch * hw;
@@ -422,31 +509,15 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     }
 
     const int npairs = na * nb;
-    const int per = (npairs + kLimbThreads - 1) / kLimbThreads;
-    const int p_begin = min(npairs, tid * per), p_end = min(npairs, p_begin + per);
-
     const long long t_start = clock64();
-    // pass 1: count the candidates of this thread's contiguous slice of (a, b) pairs
-    int cnt = 0;
-    for (int p = p_begin; p < p_end; ++p) {
-        const int a = p / nb, b = p - a * nb;
-        float s;
-        if (pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &s)) ++cnt;
-    }
-    int n;
-    int off = block_exclusive_scan(cnt, &n, scan_scratch);
-    if (n == 0) {
-        if (tid == 0) *out_cnt = 0;
-        return;
-    }
+    // Keys go to shared memory when even the upper bound (all pairs) fits, else to the pool: [npairs key slots]
+    // [2 x (npairs + 2) int32 partition scratch].
     unsigned long long* keys = sm_keys;
     int32_t *posA = nullptr, *posB = nullptr;
-    if (n > pb.cand_smem_cap) {
-        // n keys + (n + 2) entries of rank->position scratch for the block-level partition
-        const unsigned long long need = 2ull * n + 2;
-        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, need);
+    if (npairs > kSmemRange) {
+        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, (unsigned long long)npairs);
         __syncthreads();
-        if (s_pool_base + (long)need > pb.pool_cap) {
+        if (s_pool_base + (long)npairs > pb.pool_cap) {
             if (tid == 0) {
                 atomicOr(&pb.status[img], 2);
                 *out_cnt = 0;
@@ -454,20 +525,59 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
             return;
         }
         keys = pb.pool + s_pool_base;
-        posA = reinterpret_cast<int32_t*>(keys + n);
-        posB = posA + n + 2;
+        __syncthreads();
     }
-    // pass 2: keys in generation order (a-major, b-minor) = the order the reference pushes candidates in
-    for (int p = p_begin; p < p_end; ++p) {
-        const int a = p / nb, b = p - a * nb;
-        float s;
-        if (pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &s)) keys[off++] = cand_key(s, (uint32_t)p);
+    // Single pass over the (a, b) pairs in generation order (a-major, b-minor = the order the reference pushes
+    // candidates in), 512 pairs per step, ordered compaction by ballot + warp-count prefix.
+    int n = 0;
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int base = 0; base < npairs; base += kLimbThreads) {
+            const int p = base + tid;
+            float sc = 0.f;
+            bool pass = false;
+            if (p < npairs) {
+                const int a = p / nb, b = p - a * nb;
+                pass = pair_score(paf, c1, c2, ax[a], ay[a], bx[b], by[b], h_up, &sc);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) scan_scratch[warp] = __popc(m);
+            __syncthreads();
+            int pre = n, tot = 0;
+#pragma unroll
+            for (int k = 0; k < kLimbThreads / 32; ++k) {
+                const int c = scan_scratch[k];
+                if (k < warp) pre += c;
+                tot += c;
+            }
+            if (pass) keys[pre + __popc(m & ((1u << lane) - 1u))] = cand_key(sc, (uint32_t)p);
+            n += tot;
+            __syncthreads();
+        }
+    }
+    if (n == 0) {
+        if (tid == 0) *out_cnt = 0;
+        return;
+    }
+    if (npairs > kSmemRange && n > kSmemRange) {   // rank -> position scratch of the global-level partitions: n + 2 entries
+        if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, (unsigned long long)n + 2);
+        __syncthreads();
+        if (s_pool_base + n + 2 > pb.pool_cap) {
+            if (tid == 0) {
+                atomicOr(&pb.status[img], 2);
+                *out_cnt = 0;
+            }
+            return;
+        }
+        posA = reinterpret_cast<int32_t*>(pb.pool + s_pool_base);
+        posB = posA + n + 2;
     }
     for (int i = tid; i < 64; i += kLimbThreads) { used_a[i] = 0; used_b[i] = 0; }
     __threadfence();
     __syncthreads();
     const long long t_scored = clock64();
-    block_exact_sort(reinterpret_cast<uint64_t*>(keys), n, s_sort, posA, posB);     // std::sort, pafprocess.cpp:97
+    block_exact_sort(reinterpret_cast<uint64_t*>(keys), n, s_sort, reinterpret_cast<uint64_t*>(sm_keys), sm_scr, posA,
+                     posB, pb.dbg);     // std::sort, pafprocess.cpp:97
     const long long t_sorted = clock64();
     if (tid < 32) {
         const long o = ((long)img * kNumLimb + limb) * cap;
@@ -481,6 +591,8 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
                 atomicMax(pb.dbg + 2, (unsigned long long)(clock64() - t_sorted));
                 atomicMax(pb.dbg + 3, (unsigned long long)n);
                 atomicAdd(pb.dbg + 4, (unsigned long long)n);
+                atomicAdd(pb.dbg + 9, (unsigned long long)(t_sorted - t_scored));
+                atomicAdd(pb.dbg + 10, 1ull);
             }
         }
     }
@@ -670,7 +782,8 @@ cudaError_t post_limbs_and_assemble(const PostBuffers& pb, int batch, const floa
     if (batch > pb.batch_cap) return cudaErrorInvalidValue;
     B2P_TRY(cudaMemsetAsync(pb.pool_cursor, 0, sizeof(unsigned long long), s));
     PafView pv{paf, p_ch, p_y, p_x, shift};
-    size_t smem = pb.cand_smem_cap * sizeof(unsigned long long);
+    if (pb.cand_smem_cap != kSmemRange) return cudaErrorInvalidValue;
+    size_t smem = kSmemRange * sizeof(unsigned long long) + 2 * (kSmemRange + 2) * sizeof(int32_t);
     int in_smem = 0;
     if (shift == 3 && (size_t)2 * lw * lh * sizeof(float) <= 96 * 1024) {
         in_smem = 1;
