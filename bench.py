@@ -209,10 +209,10 @@ def run_ours(args):
                    "l2": "inputs rotate over 4 device buffers (208 MB > 126 MB L2); ~1.4 GB of activations per step",
                    "parallelism": "dp%d (frames sharded, one NCCL weight broadcast)" % world,
                    "post_status_bits": int(st0)},
-        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * H * W * 4,
-                "d2h_bytes_per_step": int(np.mean(d2h_bytes)) if d2h_bytes else 0,
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * H * W * 4 * world,
+                "d2h_bytes_per_step": (int(np.mean(d2h_bytes)) if d2h_bytes else 0) * world,   # rank 0's count x ranks
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "net_tflops_device": round(FLOPS_PER_FRAME * frames / (ms_dev * 1e-3) / 1e12 / world, 1),
     }
     print(json.dumps(line))

@@ -218,20 +218,37 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                 const int yo = a.pool ? y >> 1 : y;
                 const int xo = a.pool ? x >> 1 : x;
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ai * 256 + sub * 128;
+                // 32 accumulator columns per TMEM load (n_tile is a multiple of 16: a 16-column tail handles 48)
 #pragma unroll 1
-                for (int c0 = 0; c0 < a.n_tile; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + c0, r);
-                    tmem_ld_wait();
-                    float v[16];
+                for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
+                    const bool full = (c0 + 32 <= a.n_tile);
+                    uint32_t r[32];
+                    if (full) tmem_ld32(taddr + c0, r);
+                    else {
+                        uint32_t r16[16];
+                        tmem_ld16(taddr + c0, r16);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = __uint_as_float(r[j]) + __ldg(bias + c0 + j);
+                        for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0; }
+                    }
+                    float bv[32];
+                    {
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t4 = (full || j < 4) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            bv[4 * j] = t4.x; bv[4 * j + 1] = t4.y; bv[4 * j + 2] = t4.z; bv[4 * j + 3] = t4.w;
+                        }
+                    }
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __uint_as_float(r[j]) + bv[j];
                         if (a.relu) v[j] = fmaxf(v[j], 0.f);
                     }
                     if (a.pool) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < 32; ++j) {
                             v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
                             v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
                         }
@@ -240,20 +257,18 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                         if (a.out != nullptr) {
                             __nv_bfloat16* dst = a.out + (static_cast<size_t>(tc.n * Ho + yo) * Wo + xo) * a.out_cstride +
                                                  a.out_ch_off[tc.g] + ch_tile + c0;
-                            if (c0 < store_ch) {
-                                uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                     pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-                                *reinterpret_cast<uint4*>(dst) = u;
-                            }
-                            if (c0 + 8 < store_ch) {
-                                uint4 u = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]),
-                                                     pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-                                *reinterpret_cast<uint4*>(dst + 8) = u;
+#pragma unroll
+                            for (int q8 = 0; q8 < 4; ++q8) {
+                                if (c0 + 8 * q8 < store_ch) {
+                                    uint4 u = make_uint4(pack_bf16x2(v[8 * q8], v[8 * q8 + 1]), pack_bf16x2(v[8 * q8 + 2], v[8 * q8 + 3]),
+                                                         pack_bf16x2(v[8 * q8 + 4], v[8 * q8 + 5]), pack_bf16x2(v[8 * q8 + 6], v[8 * q8 + 7]));
+                                    *reinterpret_cast<uint4*>(dst + 8 * q8) = u;
+                                }
                             }
                         }
                         if (of32 != nullptr) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
+                            for (int j = 0; j < 32; ++j) {
                                 const int c = ch_tile + c0 + j;
                                 if (c < f32_ch)
                                     of32[(static_cast<size_t>(tc.n * f32_ch + c) * Ho + yo) * Wo + xo] = v[j];
