@@ -23,7 +23,13 @@ __constant__ float c_cubic[8][4] = {
     {-0x1.c5cp-4f, 0x1.a308p-1f, 0x1.5efp-2f, -0x1.9c8p-5f},  {-0x1.a94p-4f, 0x1.5918p-1f, 0x1.0568p-1f, -0x1.4acp-4f}};
 
 constexpr int kPeakThreads = 256;
-constexpr int kLimbThreads = 512;
+#ifndef B2P_LIMB_THREADS
+#define B2P_LIMB_THREADS 512
+#endif
+#ifndef B2P_SMEM_RANGE
+#define B2P_SMEM_RANGE 4096
+#endif
+constexpr int kLimbThreads = B2P_LIMB_THREADS;
 constexpr int kAsmThreads = 128;
 constexpr int kHorStride = 40;   // (2*2+1) * 8
 
@@ -180,7 +186,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
 //            and copied back.
 // Together this is exactly __introsort_loop + __final_insertion_sort, including the order of equal keys.
 constexpr int kSortQ = 128, kSortLocal = 40, kLimbWarps = kLimbThreads / 32;
-constexpr int kSmemRange = 4096, kWarpRange = 512, kBigStack = 80;
+constexpr int kSmemRange = B2P_SMEM_RANGE, kWarpRange = 512, kBigStack = 80;
 struct SortShared {
     int lock, top, pending;
     int sf[kSortQ], sl[kSortQ], sd[kSortQ];
@@ -723,7 +729,7 @@ cudaError_t post_alloc(PostBuffers& pb, int batch_cap, int peak_cap, int human_c
     pb.batch_cap = batch_cap;
     pb.peak_cap = peak_cap;
     pb.human_cap = human_cap;
-    pb.cand_smem_cap = 4096;
+    pb.cand_smem_cap = B2P_SMEM_RANGE;
     pb.pool_cap = pool_cap;
     pb.row_cap = 4 * peak_cap;
     const long B = batch_cap;
