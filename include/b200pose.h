@@ -45,6 +45,11 @@ int b200pose_net_finalize(b200pose_net* net);
  * 1 = device pointers (asynchronous on `cuda_stream`).  cuda_stream: a cudaStream_t cast to void* (NULL = default). */
 int b200pose_net_forward(b200pose_net* net, const float* input, int input_on_device, int n, int H, int W, int mode,
                          float* const* outputs, int outputs_on_device, void* cuda_stream);
+/* Same, but the input is uint8 HWC BGR frames [n,H,W,3] (what cv2.imread / crop_with_factor produce) and
+ * rtpose_preprocess (x/256 - 0.5, HWC -> CHW; lib/datasets/preprocessing.py:16-21, evaluate/coco_eval.py:93-94) is fused
+ * into the first convolution's load: 4x less H2D traffic, no fp32 staging. */
+int b200pose_net_forward_u8(b200pose_net* net, const unsigned char* images, int input_on_device, int n, int H, int W,
+                            int mode, float* const* outputs, int outputs_on_device, void* cuda_stream);
 /* Measurement hook: re-runs the launch list of the last bf16 forward (conv1_1 + 51 tensor-core launches) with a CUDA
  * event pair around every launch; fills per-launch milliseconds and ALGORITHMIC FLOPs (2 x MACs of the unpadded
  * convolution).  Returns the number of launches, < 0 on error. */
@@ -89,6 +94,9 @@ int b200pose_post_get_peaks(b200pose_post* post, int img, float* out, int max_pe
  * ---------------------------------------------------------------------------------------------------------- */
 int b200pose_infer(b200pose_net* net, b200pose_post* post, const float* input, int input_on_device, int n, int H, int W,
                    int mode, float thresh, void* cuda_stream);
+
+int b200pose_infer_u8(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device, int n,
+                      int H, int W, int mode, float thresh, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * 4. Legacy SWIG surface of lib/pafprocess (pafprocess.h:53-59, pafprocess.i:14): same names, same argument

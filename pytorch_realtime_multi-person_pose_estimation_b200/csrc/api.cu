@@ -130,9 +130,11 @@ struct b200pose_net {
     DevBuf<__nv_bfloat16> t1, t2, t3, t4, t5a, t5b, t6, t7, t8, t9, cat, bra, brb, br512;
     DevBuf<float> in_stage, out_f32[12];
     // fp32 parity buffers
-    DevBuf<float> f_a, f_b, f_cat, f_x, f_y, f_in;
+    DevBuf<float> f_a, f_b, f_cat, f_x, f_y, f_in, f_u8;
     cudaStream_t own_stream = nullptr;
-    const float* last_in = nullptr;   // device pointer of the last forward's input (profiling hook)
+    const void* last_in = nullptr;    // device pointer of the last forward's input (profiling hook)
+    int last_in_u8 = 0;
+    DevBuf<unsigned char> in_stage_u8;
 };
 
 struct b200pose_post {
@@ -252,13 +254,13 @@ int build_plan_bf16(b200pose_net* net, int n, int H, int W) {
     return 0;
 }
 
-int forward_bf16(b200pose_net* net, const float* d_in, int n, int H, int W, cudaStream_t st) {
+int forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, int W, cudaStream_t st) {
     if (net->pn != n || net->pH != H || net->pW != W || net->pmode != B200POSE_MODE_BF16) {
         CU(cudaStreamSynchronize(st));
         if (build_plan_bf16(net, n, H, W)) return 1;
         net->pn = n; net->pH = H; net->pW = W; net->pmode = B200POSE_MODE_BF16;
     }
-    CU(conv_first_launch(d_in, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st));
+    CU(conv_first_launch(d_in, in_u8, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st));
     ++g_launches;
     for (const ConvTcArgs& a : net->plan) {
         CU(conv_tc_launch(a, net->num_sms, st));
@@ -374,7 +376,8 @@ void b200pose_net_destroy(b200pose_net* net) {
     DevBuf<__nv_bfloat16>* bb[] = {&net->t1, &net->t2, &net->t3, &net->t4, &net->t5a, &net->t5b, &net->t6,
                                    &net->t7, &net->t8, &net->t9, &net->cat, &net->bra, &net->brb, &net->br512};
     for (auto* b : bb) b->release();
-    DevBuf<float>* fb[] = {&net->in_stage, &net->f_a, &net->f_b, &net->f_cat, &net->f_x, &net->f_y, &net->f_in};
+    DevBuf<float>* fb[] = {&net->in_stage, &net->f_a, &net->f_b, &net->f_cat, &net->f_x, &net->f_y, &net->f_in, &net->f_u8};
+    net->in_stage_u8.release();
     for (auto* b : fb) b->release();
     for (auto& b : net->out_f32) b.release();
     delete net;
@@ -431,20 +434,36 @@ int b200pose_net_finalize(b200pose_net* net) {
     return 0;
 }
 
-static int net_forward_impl(b200pose_net* net, const float* input, int input_on_device, int n, int H, int W, int mode,
-                            float* const* outputs, int outputs_on_device, cudaStream_t st, bool sync_host) {
+static int net_forward_impl(b200pose_net* net, const void* input, int in_u8, int input_on_device, int n, int H, int W,
+                            int mode, float* const* outputs, int outputs_on_device, cudaStream_t st, bool sync_host) {
     if (!net || !net->finalized) return fail("net not finalized");
     if (n < 1 || H < 8 || W < 8 || (H % 8) || (W % 8)) return fail("input must be [n,3,H,W] with H, W multiples of 8");
     CU(cudaSetDevice(net->device));
-    const float* d_in = input;
+    const void* d_in = input;
+    const size_t elems = (size_t)n * 3 * H * W;
     if (!input_on_device) {
-        CU(net->in_stage.ensure((size_t)n * 3 * H * W));
-        CU(cudaMemcpyAsync(net->in_stage.p, input, (size_t)n * 3 * H * W * 4, cudaMemcpyHostToDevice, st));
-        d_in = net->in_stage.p;
+        if (in_u8) {
+            CU(net->in_stage_u8.ensure(elems));
+            CU(cudaMemcpyAsync(net->in_stage_u8.p, input, elems, cudaMemcpyHostToDevice, st));
+            d_in = net->in_stage_u8.p;
+        } else {
+            CU(net->in_stage.ensure(elems));
+            CU(cudaMemcpyAsync(net->in_stage.p, input, elems * 4, cudaMemcpyHostToDevice, st));
+            d_in = net->in_stage.p;
+        }
     }
-    int rc = (mode == B200POSE_MODE_FP32) ? forward_fp32(net, d_in, n, H, W, st) : forward_bf16(net, d_in, n, H, W, st);
+    int rc;
+    if (mode == B200POSE_MODE_FP32) {
+        if (in_u8) {   // parity mode: materialise rtpose_preprocess, then the fp32 path
+            CU(net->f_u8.ensure(elems));
+            CU(u8hwc_to_f32nchw_launch(static_cast<const unsigned char*>(d_in), net->f_u8.p, n, H, W, st));
+            ++g_launches;
+            rc = forward_fp32(net, net->f_u8.p, n, H, W, st);
+        } else rc = forward_fp32(net, static_cast<const float*>(d_in), n, H, W, st);
+    } else rc = forward_bf16(net, d_in, in_u8, n, H, W, st);
     if (rc) return rc;
     net->last_in = d_in;
+    net->last_in_u8 = (mode == B200POSE_MODE_FP32) ? 0 : in_u8;
     net->pn = n; net->pH = H; net->pW = W;
     if (outputs) {
         const size_t px8 = (size_t)n * (H / 8) * (W / 8);
@@ -459,7 +478,13 @@ static int net_forward_impl(b200pose_net* net, const float* input, int input_on_
 
 int b200pose_net_forward(b200pose_net* net, const float* input, int input_on_device, int n, int H, int W, int mode,
                          float* const* outputs, int outputs_on_device, void* cuda_stream) {
-    return net_forward_impl(net, input, input_on_device, n, H, W, mode, outputs, outputs_on_device,
+    return net_forward_impl(net, input, 0, input_on_device, n, H, W, mode, outputs, outputs_on_device,
+                            reinterpret_cast<cudaStream_t>(cuda_stream), true);
+}
+
+int b200pose_net_forward_u8(b200pose_net* net, const unsigned char* images, int input_on_device, int n, int H, int W,
+                            int mode, float* const* outputs, int outputs_on_device, void* cuda_stream) {
+    return net_forward_impl(net, images, 1, input_on_device, n, H, W, mode, outputs, outputs_on_device,
                             reinterpret_cast<cudaStream_t>(cuda_stream), true);
 }
 
@@ -472,11 +497,11 @@ int b200pose_net_profile(b200pose_net* net, float* ms, double* flops, int cap, v
     if (cap < total) return -1;
     std::vector<cudaEvent_t> ev(total + 1);
     for (auto& e : ev) cudaEventCreate(&e);
-    const float* d_in = net->last_in;
+    const void* d_in = net->last_in;
     DevBuf<float> tmp;
-    if (!d_in) { if (tmp.ensure((size_t)n * 3 * H * W) != cudaSuccess) return -1; cudaMemsetAsync(tmp.p, 0, (size_t)n * 3 * H * W * 4, st); d_in = tmp.p; }
+    if (!d_in) { if (tmp.ensure((size_t)n * 3 * H * W) != cudaSuccess) return -1; cudaMemsetAsync(tmp.p, 0, (size_t)n * 3 * H * W * 4, st); d_in = tmp.p; net->last_in_u8 = 0; }
     cudaEventRecord(ev[0], st);
-    conv_first_launch(d_in, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st);
+    conv_first_launch(d_in, net->last_in_u8, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st);
     cudaEventRecord(ev[1], st);
     for (size_t i = 0; i < net->plan.size(); ++i) {
         conv_tc_launch(net->plan[i], net->num_sms, st);
@@ -641,16 +666,25 @@ int b200pose_post_get_peaks(b200pose_post* p, int img, float* out, int max_peaks
     return k;
 }
 
-int b200pose_infer(b200pose_net* net, b200pose_post* post, const float* input, int input_on_device, int n, int H, int W,
-                   int mode, float thresh, void* cuda_stream) {
+static int infer_impl(b200pose_net* net, b200pose_post* post, const void* input, int in_u8, int input_on_device, int n,
+                      int H, int W, int mode, float thresh, void* cuda_stream) {
     if (!net || !post) return fail("null handle");
     if (net->device != post->device) return fail("net and post live on different devices");
     // host input is staged asynchronously: the caller keeps it alive until b200pose_post_sync()
-    int rc = net_forward_impl(net, input, input_on_device, n, H, W, mode, nullptr, 1,
+    int rc = net_forward_impl(net, input, in_u8, input_on_device, n, H, W, mode, nullptr, 1,
                               reinterpret_cast<cudaStream_t>(cuda_stream), false);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     return post_run_dev(post, net->out_f32[11].p, net->out_f32[10].p, 0, n, H / 8, W / 8, thresh, st);
+}
+
+int b200pose_infer(b200pose_net* net, b200pose_post* post, const float* input, int input_on_device, int n, int H, int W,
+                   int mode, float thresh, void* cuda_stream) {
+    return infer_impl(net, post, input, 0, input_on_device, n, H, W, mode, thresh, cuda_stream);
+}
+int b200pose_infer_u8(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device, int n,
+                      int H, int W, int mode, float thresh, void* cuda_stream) {
+    return infer_impl(net, post, images, 1, input_on_device, n, H, W, mode, thresh, cuda_stream);
 }
 
 // ------------------------------------------------------------------------------------------------ legacy pafprocess

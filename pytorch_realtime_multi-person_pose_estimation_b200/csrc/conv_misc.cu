@@ -21,7 +21,10 @@ namespace {
 constexpr int kF_TW = 64, kF_TH = 4;        // output tile per block: 64 x 4 pixels, 2 pixels per thread
 constexpr int kF_Threads = 128;
 
-__global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
+// kU8 = true: `in` is uint8 HWC BGR [N,H,W,3] and rtpose_preprocess (x/256 - 0.5, HWC -> CHW;
+// /root/reference/lib/datasets/preprocessing.py:16-21) is fused into the tile load.
+template <bool kU8>
+__global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const void* __restrict__ in_v, const float* __restrict__ wgt,
                                                                 const float* __restrict__ bias,
                                                                 __nv_bfloat16* __restrict__ out, int H, int W) {
     __shared__ float s_in[3][kF_TH + 2][kF_TW + 2];
@@ -35,13 +38,30 @@ __global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const float* __r
         s_w[k][o] = wgt[o * 27 + k];
     }
     if (tid < 64) s_b[tid] = bias[tid];
-    const float* inp = in + (size_t)n * 3 * H * W;
     for (int i = tid; i < 3 * (kF_TH + 2) * (kF_TW + 2); i += kF_Threads) {
-        const int c = i / ((kF_TH + 2) * (kF_TW + 2));
-        const int r = i - c * (kF_TH + 2) * (kF_TW + 2);
-        const int yy = r / (kF_TW + 2), xx = r - yy * (kF_TW + 2);
+        int c, yy, xx;
+        if (kU8) {   // channel fastest: consecutive threads read consecutive bytes
+            c = i % 3;
+            const int r = i / 3;
+            yy = r / (kF_TW + 2);
+            xx = r - yy * (kF_TW + 2);
+        } else {
+            c = i / ((kF_TH + 2) * (kF_TW + 2));
+            const int r = i - c * (kF_TH + 2) * (kF_TW + 2);
+            yy = r / (kF_TW + 2);
+            xx = r - yy * (kF_TW + 2);
+        }
         const int gy = y0 + yy - 1, gx = x0 + xx - 1;
-        s_in[c][yy][xx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? inp[((size_t)c * H + gy) * W + gx] : 0.f;
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            if (kU8) {
+                const unsigned char u = static_cast<const unsigned char*>(in_v)[(((size_t)n * H + gy) * W + gx) * 3 + c];
+                v = __fadd_rn(__fdiv_rn((float)u, 256.f), -0.5f);
+            } else {
+                v = static_cast<const float*>(in_v)[(((size_t)n * 3 + c) * H + gy) * W + gx];
+            }
+        }
+        s_in[c][yy][xx] = v;
     }
     __syncthreads();
     const int ty = tid >> 5, tx = (tid & 31) * 2;     // 4 rows x 32 pixel pairs
@@ -198,10 +218,33 @@ __global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ in, float* __r
 
 }  // namespace
 
-cudaError_t conv_first_launch(const float* in_nchw, const float* w_oihw, const float* bias, __nv_bfloat16* out_nhwc,
-                              int N, int H, int W, cudaStream_t s) {
+cudaError_t conv_first_launch(const void* in, int in_is_u8_hwc, const float* w_oihw, const float* bias,
+                              __nv_bfloat16* out_nhwc, int N, int H, int W, cudaStream_t s) {
     dim3 grid((W + kF_TW - 1) / kF_TW, (H + kF_TH - 1) / kF_TH, N);
-    conv_first_kernel<<<grid, kF_Threads, 0, s>>>(in_nchw, w_oihw, bias, out_nhwc, H, W);
+    if (in_is_u8_hwc) conv_first_kernel<true><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, H, W);
+    else conv_first_kernel<false><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, H, W);
+    return cudaGetLastError();
+}
+
+namespace {
+__global__ void u8hwc_to_f32nchw_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, int N, int H, int W) {
+    const size_t total = (size_t)N * 3 * H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = i % W;
+        size_t t = i / W;
+        const int y = t % H;
+        t /= H;
+        const int c = t % 3;
+        const int n = t / 3;
+        out[i] = __fadd_rn(__fdiv_rn((float)in[(((size_t)n * H + y) * W + x) * 3 + c], 256.f), -0.5f);
+    }
+}
+}  // namespace
+
+cudaError_t u8hwc_to_f32nchw_launch(const unsigned char* in, float* out, int N, int H, int W, cudaStream_t s) {
+    const size_t total = (size_t)N * 3 * H * W;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    u8hwc_to_f32nchw_kernel<<<blocks, 256, 0, s>>>(in, out, N, H, W);
     return cudaGetLastError();
 }
 

@@ -102,35 +102,48 @@ __global__ void __launch_bounds__(kPeakThreads) peaks_kernel(PostBuffers pb, con
         const int pw = x_max - x_min + 1, ph = y_max - y_min + 1;
         const int W8 = pw * 8, H8 = ph * 8;
         __syncwarp();
-        for (int idx = lane; idx < ph * W8; idx += 32) {
-            const int r = idx / W8, X = idx - r * W8;
-            const int phase = X & 7;
-            const int sx = (X >> 3) + (phase < 4 ? -2 : -1);
-            const float* prow = plane + (y_min + r) * w + x_min;
-            const float s0 = prow[clampi(sx, 0, pw - 1)], s1 = prow[clampi(sx + 1, 0, pw - 1)];
-            const float s2 = prow[clampi(sx + 2, 0, pw - 1)], s3 = prow[clampi(sx + 3, 0, pw - 1)];
-            float v = __fmul_rn(s0, c_cubic[phase][0]);
-            v = __fadd_rn(v, __fmul_rn(s1, c_cubic[phase][1]));
-            v = __fadd_rn(v, __fmul_rn(s2, c_cubic[phase][2]));
-            v = __fadd_rn(v, __fmul_rn(s3, c_cubic[phase][3]));
-            hor[r * kHorStride + X] = v;
+        // horizontal pass: lanes own columns X = lane and lane + 32 (W8 <= 40), rows are walked - no divisions
+        for (int xi = 0; xi < 2; ++xi) {
+            const int X = lane + 32 * xi;
+            if (X < W8) {
+                const int phase = X & 7;
+                const int sx = (X >> 3) + (phase < 4 ? -2 : -1);
+                const int t0 = clampi(sx, 0, pw - 1), t1 = clampi(sx + 1, 0, pw - 1);
+                const int t2 = clampi(sx + 2, 0, pw - 1), t3 = clampi(sx + 3, 0, pw - 1);
+                const float a0 = c_cubic[phase][0], a1 = c_cubic[phase][1], a2 = c_cubic[phase][2], a3 = c_cubic[phase][3];
+                for (int r = 0; r < ph; ++r) {
+                    const float* prow = plane + (y_min + r) * w + x_min;
+                    float v = __fmul_rn(prow[t0], a0);
+                    v = __fadd_rn(v, __fmul_rn(prow[t1], a1));
+                    v = __fadd_rn(v, __fmul_rn(prow[t2], a2));
+                    v = __fadd_rn(v, __fmul_rn(prow[t3], a3));
+                    hor[r * kHorStride + X] = v;
+                }
+            }
         }
         __syncwarp();
+        // vertical pass + first arg-max (row-major index Y*W8 + X; each lane visits its indices in increasing order)
         float best = -INFINITY;
         int best_idx = 0x7fffffff;
-        for (int idx = lane; idx < H8 * W8; idx += 32) {
-            const int Y = idx / W8, X = idx - Y * W8;
+        for (int Y = 0; Y < H8; ++Y) {
             const int phase = Y & 7;
             const int sy = (Y >> 3) + (phase < 4 ? -2 : -1);
-            const float S0 = hor[clampi(sy, 0, ph - 1) * kHorStride + X];
-            const float S1 = hor[clampi(sy + 1, 0, ph - 1) * kHorStride + X];
-            const float S2 = hor[clampi(sy + 2, 0, ph - 1) * kHorStride + X];
-            const float S3 = hor[clampi(sy + 3, 0, ph - 1) * kHorStride + X];
-            float v = __fmul_rn(S3, c_cubic[phase][3]);
-            v = __fadd_rn(__fmul_rn(S2, c_cubic[phase][2]), v);
-            v = __fadd_rn(__fmul_rn(S1, c_cubic[phase][1]), v);
-            v = __fadd_rn(__fmul_rn(S0, c_cubic[phase][0]), v);
-            if (v > best) { best = v; best_idx = idx; }
+            const float* h0 = hor + clampi(sy, 0, ph - 1) * kHorStride;
+            const float* h1 = hor + clampi(sy + 1, 0, ph - 1) * kHorStride;
+            const float* h2 = hor + clampi(sy + 2, 0, ph - 1) * kHorStride;
+            const float* h3 = hor + clampi(sy + 3, 0, ph - 1) * kHorStride;
+            const float b0 = c_cubic[phase][0], b1 = c_cubic[phase][1], b2 = c_cubic[phase][2], b3 = c_cubic[phase][3];
+#pragma unroll
+            for (int xi = 0; xi < 2; ++xi) {
+                const int X = lane + 32 * xi;
+                if (X < W8) {
+                    float v = __fmul_rn(h3[X], b3);
+                    v = __fadd_rn(__fmul_rn(h2[X], b2), v);
+                    v = __fadd_rn(__fmul_rn(h1[X], b1), v);
+                    v = __fadd_rn(__fmul_rn(h0[X], b0), v);
+                    if (v > best) { best = v; best_idx = Y * W8 + X; }
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -373,7 +386,7 @@ __device__ void smem_sort_range(uint64_t* w, int f, int l, int d, SortShared& sh
         if (state == 2) break;
         if (state == 0) {
             if (++idle > (1u << 24)) { printf("[b200pose] exact sort: idle watchdog (block %d,%d)\n", (int)blockIdx.x, (int)blockIdx.y); __trap(); }
-            __nanosleep(100);
+            __nanosleep(1000);
             continue;
         }
         idle = 0;

@@ -33,6 +33,13 @@ class NativeNet:
         nat.check(nat.lib().b200pose_net_forward(self._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H, W, mode,
                                                  arr, int(out_on_device), ctypes.c_void_p(stream)), "b200pose_net_forward")
 
+    def forward_u8_ptr(self, in_ptr, in_on_device, n, H, W, mode, out_ptrs, out_on_device, stream):
+        """uint8 HWC BGR frames [n,H,W,3]; rtpose_preprocess is fused into the first convolution."""
+        arr = (ctypes.c_void_p * 12)(*[ctypes.c_void_p(p) if p else None for p in out_ptrs])
+        nat.check(nat.lib().b200pose_net_forward_u8(self._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H, W, mode,
+                                                    arr, int(out_on_device), ctypes.c_void_p(stream)),
+                  "b200pose_net_forward_u8")
+
     def __del__(self):
         try:
             if self._h:
@@ -127,6 +134,13 @@ class PoseEngine:
                                            self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)), "b200pose_infer")
         self._last = (n, H, W)
 
+    def infer_async_u8(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
+        """uint8 HWC BGR frames [n,H,W,3] (host pinned or device); preprocessing runs on the device."""
+        nat.check(nat.lib().b200pose_infer_u8(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H,
+                                              W, self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
+                  "b200pose_infer_u8")
+        self._last = (n, H, W)
+
     def fetch(self, check=True):
         n, H, W = self._last
         self.post.sync()
@@ -135,8 +149,14 @@ class PoseEngine:
         return [humans_to_dicts(self.post.humans(i), W, H) for i in range(n)]
 
     def infer_batch(self, images, thresh=0.1):
-        """images: float32 numpy [n,3,H,W] (host) or a CUDA torch tensor.  Returns per-image human lists."""
-        if isinstance(images, np.ndarray):
+        """images: uint8 numpy [n,H,W,3] (BGR frames, preprocessing fused on the device), float32 numpy [n,3,H,W]
+        (already preprocessed, host) or a CUDA float tensor.  Returns per-image human lists."""
+        if isinstance(images, np.ndarray) and images.dtype == np.uint8:
+            images = np.ascontiguousarray(images)
+            n, H, W, _ = images.shape          # [n,H,W,3] BGR, already cropped/padded to multiples of 8
+            self._keep = images
+            self.infer_async_u8(images.ctypes.data, False, n, H, W, thresh)
+        elif isinstance(images, np.ndarray):
             images = np.ascontiguousarray(images, dtype=np.float32)
             n, _, H, W = images.shape
             self._keep = images

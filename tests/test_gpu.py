@@ -217,3 +217,23 @@ def test_fused_engine_matches_stagewise(built, he_sd):
         _, want = glue_port.paf_to_pose(heat, paf, port)
         assert_humans_equal(fused[i], want, score_tol=0.0)
     assert pkg_module("_native").launch_count() > 0
+
+
+def test_uint8_input_path_fuses_rtpose_preprocess(native_net, he_sd):
+    """b200pose_net_forward_u8 (uint8 HWC BGR frames, preprocessing fused into conv1_1) must give the very same maps as
+    rtpose_preprocess on the host + the fp32-input entry point, in both modes, and match the oracle in fp32 mode."""
+    nat = pkg_module("_native")
+    img = np.random.RandomState(11).randint(0, 256, (2, 64, 72, 3)).astype(np.uint8)
+    x = torch.from_numpy(np.stack([glue_port.rtpose_preprocess(i) for i in img]))
+    xd = torch.from_numpy(img).cuda()
+    for mode in ("bf16", "fp32"):
+        ref = _forward(native_net, x, mode)
+        outs = [torch.empty((2, 38 if i % 2 == 0 else 19, 8, 9), device="cuda") for i in range(12)]
+        native_net.forward_u8_ptr(xd.data_ptr(), True, 2, 64, 72, nat.MODES[mode], [o.data_ptr() for o in outs], True,
+                                  torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        for a, b in zip(outs, ref):
+            assert torch.equal(a.cpu(), b)
+    with torch.no_grad():
+        _, saved = net_port.forward(he_sd, x)
+    assert max(float((o.cpu() - s).abs().max()) for o, s in zip(outs, saved)) < FP32_TOL
