@@ -102,7 +102,7 @@ def run_ours(args):
         arrays = dist_mod.broadcast_state_arrays(synthetic_weights() if rank == 0 else None, device=dev)
     else:
         arrays = synthetic_weights()
-    eng = engine.PoseEngine(arrays, local, mode="bf16", batch_cap=BATCH, peak_cap=1024, human_cap=1024)
+    eng = engine.PoseEngine(arrays, local, mode="bf16", batch_cap=BATCH, peak_cap=1024, human_cap=512)
 
     # Frames are uint8 HWC BGR (what cv2.imread / crop_with_factor hand to get_outputs); rtpose_preprocess is fused
     # into the first convolution.  10 rotating device batches (10 x 13 MB > 126 MB L2) + 2 pinned host batches.
@@ -122,13 +122,17 @@ def run_ours(args):
 
     d2h_bytes = []
 
-    def step_e2e(i):
-        eng.infer_async_u8(host[i % 2].data_ptr(), False, BATCH, H, W, 0.1, sptr)
-        eng.post.sync()
+    def submit_e2e(i):
+        return eng.infer_async_u8(host[i % 2].data_ptr(), False, BATCH, H, W, 0.1, sptr)
+
+    def fetch_e2e(ticket):
+        eng.post.select(ticket)
         nh = 0
         for k in range(BATCH):
             nh += len(eng.post.humans(k))
-        d2h_bytes.append(4 * BATCH * (1 + 1 + 18) + nh * 73 * 4)
+        # what actually crosses PCIe per step: counts/status/n_humans + the full-capacity person buffer
+        d2h_bytes.append(4 * BATCH * (1 + 1 + 18) + BATCH * eng.post.human_cap * 73 * 4)
+        return nh
 
     for i in range(args.warmup):
         step_device(i)
@@ -143,6 +147,7 @@ def run_ours(args):
     e0.record(stream)
     for i in range(args.steps):
         step_device(i)
+    eng.post.sync()          # the last step's assembly + result copy run on the engine's second stream
     e1.record(stream)
     torch.cuda.synchronize()
     ms_dev = e0.elapsed_time(e1)
@@ -150,15 +155,20 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     barrier()
 
-    # ---- end-to-end timing through the public API with host buffers (e2e)
-    for i in range(2):
-        step_e2e(i)
+    # ---- end-to-end timing through the public API with host buffers (e2e): every step copies its uint8 frames from
+    # pinned host memory and its results back; two runs are kept in flight (submit i+1, then read i), K results are read
+    # inside the timed region.
+    fetch_e2e(submit_e2e(0))
     d2h_bytes.clear()
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(args.steps):
-        step_e2e(i)
+    pending = submit_e2e(0)
+    for i in range(1, args.steps):
+        nxt = submit_e2e(i)
+        fetch_e2e(pending)
+        pending = nxt
+    fetch_e2e(pending)
     e1.record(stream)
     torch.cuda.synchronize()
     ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)

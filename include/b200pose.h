@@ -77,7 +77,14 @@ void b200pose_post_destroy(b200pose_post* post);
  * thresh = cfg.TEST.THRESH_HEATMAP.  Results stay on the device until fetched. */
 int b200pose_post_run(b200pose_post* post, const float* heat, const float* paf, int on_device, int layout, int n, int h,
                       int w, float thresh, void* cuda_stream);
-/* Blocks until the stream work of the last run finished and results are on the host. */
+/* Every run copies its results (person rows, counts, status) to pinned host memory by itself, on a second stream right
+ * after the person assembly, into one of two slots (run parity) - so a caller may submit run i+1 before reading run i
+ * (at most two runs in flight).  The getters below read the selected slot.
+ *   b200pose_post_last_ticket : ticket (0-based index) of the most recently submitted run, -1 if none
+ *   b200pose_post_select      : block until run `ticket` is on the host and make the getters read it
+ *   b200pose_post_sync        : select(last ticket) */
+long b200pose_post_last_ticket(b200pose_post* post);
+int b200pose_post_select(b200pose_post* post, long ticket);
 int b200pose_post_sync(b200pose_post* post);
 /* Diagnostics: out[0..2] = max SM cycles of the limbs kernel phases (scoring, exact sort, greedy) over all blocks since
  * the last reset, out[3] = max candidates of a limb, out[4] = total candidates. */

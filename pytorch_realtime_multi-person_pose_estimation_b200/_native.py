@@ -44,6 +44,8 @@ def lib():
         "b200pose_post_destroy": ([vp], None),
         "b200pose_post_run": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
         "b200pose_post_sync": ([vp], ci),
+        "b200pose_post_last_ticket": ([vp], cl),
+        "b200pose_post_select": ([vp, cl], ci),
         "b200pose_post_debug": ([vp, vp, ci, ci], ci),
         "b200pose_post_num_humans": ([vp, ci], ci),
         "b200pose_post_status": ([vp, ci], ci),
@@ -70,7 +72,7 @@ def lib():
 EXPORTED = ["b200pose_last_error", "b200pose_version", "b200pose_launch_count", "b200pose_net_create",
             "b200pose_net_destroy", "b200pose_net_tensor_shape", "b200pose_net_set_tensor", "b200pose_net_finalize",
             "b200pose_net_forward", "b200pose_net_forward_u8", "b200pose_net_profile", "b200pose_net_last_maps", "b200pose_post_create", "b200pose_post_destroy",
-            "b200pose_post_run", "b200pose_post_sync", "b200pose_post_debug", "b200pose_post_num_humans", "b200pose_post_status",
+            "b200pose_post_run", "b200pose_post_sync", "b200pose_post_last_ticket", "b200pose_post_select", "b200pose_post_debug", "b200pose_post_num_humans", "b200pose_post_status",
             "b200pose_post_get_humans", "b200pose_post_get_peaks", "b200pose_infer", "b200pose_infer_u8", "process_paf", "get_num_humans",
             "get_part_cid", "get_score", "get_part_x", "get_part_y", "get_part_score"]
 

@@ -141,13 +141,22 @@ struct b200pose_post {
     int device = 0;
     PostBuffers pb{};
     DevBuf<float> d_heat, d_paf;
-    std::vector<int> h_nh, h_status, h_counts;
-    std::vector<float> h_humans, h_px_s;
+    // Results are copied to pinned host memory by the run itself (second stream, right after the assembly) into one
+    // of two slots selected by the run's parity, so the host can fetch run i while run i+1 is in flight.
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_limbs = nullptr, ev_asm = nullptr, ev_fetch[2] = {nullptr, nullptr};
+    bool have_asm = false;
+    long runs = 0;                  // runs submitted so far; ticket of the latest = runs - 1
+    int slot_n[2] = {0, 0};
+    int* hp_nh[2] = {nullptr, nullptr};
+    int* hp_status[2] = {nullptr, nullptr};
+    int* hp_counts[2] = {nullptr, nullptr};
+    float* hp_humans[2] = {nullptr, nullptr};
+    int cur = 0;                    // slot the getters read
+    long cur_ticket = -1;
+    std::vector<float> h_px_s;
     std::vector<int> h_px, h_py;
-    int last_n = 0, hw_h = 0, hw_w = 0;
-    bool fetched = false;
-    cudaStream_t last_stream = nullptr;
-    cudaEvent_t done = nullptr;
+    int hw_h = 0, hw_w = 0;
 };
 
 namespace {
@@ -537,7 +546,16 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
     const long pool = (long)batch_cap * (6L << 20) < (1L << 28) ? (long)batch_cap * (6L << 20) : (1L << 28);
     cudaError_t e = post_alloc(p->pb, batch_cap, peak_cap, human_cap, pool);
     if (e != cudaSuccess) { delete p; return fail("post_alloc failed: %s", cudaGetErrorString(e)); }
-    CU(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&p->ev_limbs, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&p->ev_asm, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        CU(cudaEventCreateWithFlags(&p->ev_fetch[b], cudaEventDisableTiming));
+        CU(cudaHostAlloc(&p->hp_nh[b], (size_t)batch_cap * sizeof(int), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&p->hp_status[b], (size_t)batch_cap * sizeof(int), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&p->hp_counts[b], (size_t)batch_cap * 18 * sizeof(int), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&p->hp_humans[b], (size_t)batch_cap * human_cap * kHumanFloats * sizeof(float), cudaHostAllocDefault));
+    }
     *out = p;
     return 0;
 }
@@ -545,30 +563,64 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
 void b200pose_post_destroy(b200pose_post* p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    if (p->s2) cudaStreamSynchronize(p->s2);
     post_free(p->pb);
     p->d_heat.release(); p->d_paf.release();
-    if (p->done) cudaEventDestroy(p->done);
+    for (int b = 0; b < 2; ++b) {
+        if (p->ev_fetch[b]) cudaEventDestroy(p->ev_fetch[b]);
+        if (p->hp_nh[b]) cudaFreeHost(p->hp_nh[b]);
+        if (p->hp_status[b]) cudaFreeHost(p->hp_status[b]);
+        if (p->hp_counts[b]) cudaFreeHost(p->hp_counts[b]);
+        if (p->hp_humans[b]) cudaFreeHost(p->hp_humans[b]);
+    }
+    if (p->ev_limbs) cudaEventDestroy(p->ev_limbs);
+    if (p->ev_asm) cudaEventDestroy(p->ev_asm);
+    if (p->s2) cudaStreamDestroy(p->s2);
     delete p;
+}
+
+// After the limbs kernel was enqueued on `st`: assembly + result copies on the second stream.
+static int enqueue_assemble_and_fetch(b200pose_post* p, int n, cudaStream_t st) {
+    CU(cudaEventRecord(p->ev_limbs, st));
+    CU(cudaStreamWaitEvent(p->s2, p->ev_limbs, 0));
+    cudaError_t e = post_assemble(p->pb, n, p->s2);
+    if (e != cudaSuccess) return fail("post_assemble: %s", cudaGetErrorString(e));
+    ++g_launches;
+    CU(cudaEventRecord(p->ev_asm, p->s2));
+    p->have_asm = true;
+    const int b = (int)(p->runs & 1);
+    const PostBuffers& pb = p->pb;
+    CU(cudaMemcpyAsync(p->hp_nh[b], pb.n_humans, n * sizeof(int), cudaMemcpyDeviceToHost, p->s2));
+    CU(cudaMemcpyAsync(p->hp_status[b], pb.status, n * sizeof(int), cudaMemcpyDeviceToHost, p->s2));
+    CU(cudaMemcpyAsync(p->hp_counts[b], pb.counts, (size_t)n * 18 * sizeof(int), cudaMemcpyDeviceToHost, p->s2));
+    CU(cudaMemcpyAsync(p->hp_humans[b], pb.humans, (size_t)n * pb.human_cap * kHumanFloats * sizeof(float),
+                       cudaMemcpyDeviceToHost, p->s2));
+    CU(cudaEventRecord(p->ev_fetch[b], p->s2));
+    p->slot_n[b] = n;
+    p->runs += 1;
+    p->h_px.clear();
+    return 0;
 }
 
 static int post_run_dev(b200pose_post* p, const float* d_heat, const float* d_paf, int layout, int n, int h, int w,
                         float thresh, cudaStream_t st) {
     if (n > p->pb.batch_cap) return fail("batch %d exceeds post batch_cap %d", n, p->pb.batch_cap);
+    // the previous run's assembly (second stream) still reads the peak / connection buffers this run overwrites
+    if (p->have_asm) CU(cudaStreamWaitEvent(st, p->ev_asm, 0));
     cudaError_t e;
     if (layout == 0) {
         e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, (long)h * w, w, 1, h, w, thresh, st);
         if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
-        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, (long)h * w, w, 1, 3, h * 8, w, h, st);
+        e = post_limbs(p->pb, n, d_paf, (long)38 * h * w, (long)h * w, w, 1, 3, h * 8, w, h, st);
     } else {
         e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, 1, (long)w * 19, 19, h, w, thresh, st);
         if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
-        e = post_limbs_and_assemble(p->pb, n, d_paf, (long)38 * h * w, 1, (long)w * 38, 38, 3, h * 8, w, h, st);
+        e = post_limbs(p->pb, n, d_paf, (long)38 * h * w, 1, (long)w * 38, 38, 3, h * 8, w, h, st);
     }
-    if (e != cudaSuccess) return fail("post_limbs_and_assemble: %s", cudaGetErrorString(e));
-    g_launches += 3;
-    p->last_n = n; p->hw_h = h; p->hw_w = w; p->fetched = false; p->last_stream = st;
-    CU(cudaEventRecord(p->done, st));
-    return 0;
+    if (e != cudaSuccess) return fail("post_limbs: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    p->hw_h = h; p->hw_w = w;
+    return enqueue_assemble_and_fetch(p, n, st);
 }
 
 int b200pose_post_run(b200pose_post* p, const float* heat, const float* paf, int on_device, int layout, int n, int h,
@@ -587,30 +639,22 @@ int b200pose_post_run(b200pose_post* p, const float* heat, const float* paf, int
     return post_run_dev(p, dh, dp, layout, n, h, w, thresh, st);
 }
 
+long b200pose_post_last_ticket(b200pose_post* p) { return p ? p->runs - 1 : -1; }
+
+int b200pose_post_select(b200pose_post* p, long ticket) {
+    if (!p) return fail("null post");
+    if (ticket < 0 || ticket >= p->runs || ticket < p->runs - 2) return fail("ticket %ld is not one of the last two runs", ticket);
+    CU(cudaSetDevice(p->device));
+    CU(cudaEventSynchronize(p->ev_fetch[ticket & 1]));
+    p->cur = (int)(ticket & 1);
+    p->cur_ticket = ticket;
+    return 0;
+}
+
 int b200pose_post_sync(b200pose_post* p) {
     if (!p) return fail("null post");
-    if (p->fetched) return 0;
-    CU(cudaSetDevice(p->device));
-    const int n = p->last_n;
-    const PostBuffers& pb = p->pb;
-    cudaStream_t st = p->last_stream;
-    p->h_nh.resize(n); p->h_status.resize(n); p->h_counts.resize((size_t)n * 18);
-    CU(cudaMemcpyAsync(p->h_nh.data(), pb.n_humans, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(p->h_status.data(), pb.status, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(p->h_counts.data(), pb.counts, (size_t)n * 18 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    int max_h = 0;
-    for (int i = 0; i < n; ++i) max_h = p->h_nh[i] > max_h ? p->h_nh[i] : max_h;
-    p->h_humans.resize((size_t)n * pb.human_cap * kHumanFloats);
-    for (int i = 0; i < n; ++i)
-        if (p->h_nh[i] > 0)
-            CU(cudaMemcpyAsync(p->h_humans.data() + (size_t)i * pb.human_cap * kHumanFloats,
-                               pb.humans + (size_t)i * pb.human_cap * kHumanFloats,
-                               (size_t)p->h_nh[i] * kHumanFloats * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    p->h_px.clear();   // peaks are fetched lazily by get_peaks
-    p->fetched = true;
-    return 0;
+    if (p->runs == 0) return fail("no run submitted");
+    return b200pose_post_select(p, p->runs - 1);
 }
 
 int b200pose_post_debug(b200pose_post* p, unsigned long long* out, int n, int reset) {
@@ -619,30 +663,28 @@ int b200pose_post_debug(b200pose_post* p, unsigned long long* out, int n, int re
     if (reset) cudaMemset(p->pb.dbg, 0, 16 * sizeof(unsigned long long));
     return 0;
 }
-int b200pose_post_num_humans(b200pose_post* p, int img) {
-    if (b200pose_post_sync(p)) return -1;
-    if (img < 0 || img >= p->last_n) return -1;
-    return p->h_nh[img];
+static int post_ready(b200pose_post* p, int img) {
+    if (!p) return 0;
+    if (p->cur_ticket < 0 && b200pose_post_sync(p)) return 0;
+    return img >= 0 && img < p->slot_n[p->cur];
 }
-int b200pose_post_status(b200pose_post* p, int img) {
-    if (b200pose_post_sync(p)) return -1;
-    if (img < 0 || img >= p->last_n) return -1;
-    return p->h_status[img];
-}
+int b200pose_post_num_humans(b200pose_post* p, int img) { return post_ready(p, img) ? p->hp_nh[p->cur][img] : -1; }
+int b200pose_post_status(b200pose_post* p, int img) { return post_ready(p, img) ? p->hp_status[p->cur][img] : -1; }
 int b200pose_post_get_humans(b200pose_post* p, int img, float* out, int max_humans) {
-    if (b200pose_post_sync(p)) return -1;
-    if (img < 0 || img >= p->last_n) return -1;
-    const int n = p->h_nh[img] < max_humans ? p->h_nh[img] : max_humans;
-    memcpy(out, p->h_humans.data() + (size_t)img * p->pb.human_cap * kHumanFloats, (size_t)n * kHumanFloats * sizeof(float));
+    if (!post_ready(p, img)) return -1;
+    const int n = p->hp_nh[p->cur][img] < max_humans ? p->hp_nh[p->cur][img] : max_humans;
+    memcpy(out, p->hp_humans[p->cur] + (size_t)img * p->pb.human_cap * kHumanFloats, (size_t)n * kHumanFloats * sizeof(float));
     return n;
 }
 int b200pose_post_get_peaks(b200pose_post* p, int img, float* out, int max_peaks) {
-    if (b200pose_post_sync(p)) return -1;
-    if (img < 0 || img >= p->last_n) return -1;
+    // valid for the LATEST run only (reads the device peak arrays, which the next run overwrites)
+    if (!p || p->runs == 0 || b200pose_post_select(p, p->runs - 1)) return -1;
+    const int last_n = p->slot_n[p->cur];
+    if (img < 0 || img >= last_n) return -1;
     const PostBuffers& pb = p->pb;
     const size_t per = (size_t)18 * pb.peak_cap;
     if (p->h_px.empty()) {
-        const size_t tot = per * p->last_n;
+        const size_t tot = per * last_n;
         p->h_px.resize(tot); p->h_py.resize(tot); p->h_px_s.resize(tot);
         if (cudaMemcpy(p->h_px.data(), pb.peak_x, tot * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
             cudaMemcpy(p->h_py.data(), pb.peak_y, tot * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -653,7 +695,7 @@ int b200pose_post_get_peaks(b200pose_post* p, int img, float* out, int max_peaks
     }
     int k = 0;
     for (int part = 0; part < 18; ++part) {
-        const int c = p->h_counts[(size_t)img * 18 + part];
+        const int c = p->hp_counts[p->cur][(size_t)img * 18 + part];
         for (int i = 0; i < c && k < max_peaks; ++i, ++k) {
             const size_t o = (size_t)img * per + (size_t)part * pb.peak_cap + i;
             out[5 * k + 0] = (float)p->h_px[o];
@@ -738,14 +780,15 @@ int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, fl
     CU(cudaMemcpyAsync(pb.peak_s, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, st));
     CU(p->d_paf.ensure((size_t)f1 * f2 * f3));
     CU(cudaMemcpyAsync(p->d_paf.p, pafmap, (size_t)f1 * f2 * f3 * 4, cudaMemcpyHostToDevice, st));
-    cudaError_t e = post_limbs_and_assemble(pb, 1, p->d_paf.p, 0, 1, (long)f2 * f3, f3, 0, h1, f2, f1, st);
-    if (e != cudaSuccess) return fail("post_limbs_and_assemble: %s", cudaGetErrorString(e));
-    g_launches += 2;
-    p->last_n = 1; p->fetched = false; p->last_stream = st;
+    if (p->have_asm) CU(cudaStreamWaitEvent(st, p->ev_asm, 0));
+    cudaError_t e = post_limbs(pb, 1, p->d_paf.p, 0, 1, (long)f2 * f3, f3, 0, h1, f2, f1, st);
+    if (e != cudaSuccess) return fail("post_limbs: %s", cudaGetErrorString(e));
+    ++g_launches;
+    if (enqueue_assemble_and_fetch(p, 1, st)) return 3;
     if (b200pose_post_sync(p)) return 3;
-    if (p->h_status[0] & 0xff & ~16) return fail("process_paf: capacity exceeded (status %d)", p->h_status[0]);
-    g_leg_nh = p->h_nh[0];
-    g_leg_humans.assign(p->h_humans.begin(), p->h_humans.begin() + (size_t)g_leg_nh * kHumanFloats);
+    if (p->hp_status[p->cur][0] & 0xff & ~16) return fail("process_paf: capacity exceeded (status %d)", p->hp_status[p->cur][0]);
+    g_leg_nh = p->hp_nh[p->cur][0];
+    g_leg_humans.assign(p->hp_humans[p->cur], p->hp_humans[p->cur] + (size_t)g_leg_nh * kHumanFloats);
     return 0;
 }
 int get_num_humans(void) { return g_leg_nh; }

@@ -796,7 +796,7 @@ cudaError_t post_peaks(const PostBuffers& pb, int batch, const float* heat, long
     return cudaGetLastError();
 }
 
-cudaError_t post_limbs_and_assemble(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
+cudaError_t post_limbs(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
                                     long p_x, int shift, int h_up, int lw, int lh, cudaStream_t s) {
     if (batch > pb.batch_cap) return cudaErrorInvalidValue;
     B2P_TRY(cudaMemsetAsync(pb.pool_cursor, 0, sizeof(unsigned long long), s));
@@ -814,7 +814,11 @@ cudaError_t post_limbs_and_assemble(const PostBuffers& pb, int batch, const floa
         smem_set = smem;
     }
     limbs_kernel<<<dim3(kNumLimb, batch), kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem);
-    B2P_TRY(cudaGetLastError());
+    return cudaGetLastError();
+}
+
+cudaError_t post_assemble(const PostBuffers& pb, int batch, cudaStream_t s) {
+    if (batch > pb.batch_cap) return cudaErrorInvalidValue;
     assemble_kernel<<<batch, kAsmThreads, pb.human_cap * sizeof(int), s>>>(pb);
     return cudaGetLastError();
 }

@@ -52,8 +52,11 @@ void post_free(PostBuffers& pb);
 cudaError_t post_peaks(const PostBuffers& pb, int batch, const float* heat, long h_img, long h_ch, long h_y, long h_x,
                        int h, int w, float thresh, cudaStream_t s);
 // paf: fp32 view per image: base + img*p_img, strides (p_ch, p_y, p_x), shift (3: low-res, 0: already upsampled).
-cudaError_t post_limbs_and_assemble(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
+cudaError_t post_limbs(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
                                     long p_x, int shift, int h_up, int lw, int lh, cudaStream_t s);
+// Person assembly of the connections post_limbs() left in `pb`.  Small footprint (128 threads, human_cap*4 B smem per
+// image): it can run on a second stream next to the convolutions of the following batch.
+cudaError_t post_assemble(const PostBuffers& pb, int batch, cudaStream_t s);
 // lw x lh: dimensions of the low-resolution PAF planes (used to stage them in shared memory when shift == 3)
 
 }  // namespace b2p

@@ -66,6 +66,13 @@ class NativePost:
     def sync(self):
         nat.check(nat.lib().b200pose_post_sync(self._h), "b200pose_post_sync")
 
+    def last_ticket(self):
+        return int(nat.lib().b200pose_post_last_ticket(self._h))
+
+    def select(self, ticket):
+        """Wait for run `ticket` (one of the last two submitted) and make the getters read its results."""
+        nat.check(nat.lib().b200pose_post_select(self._h, int(ticket)), "b200pose_post_select")
+
     def status(self, img):
         return int(nat.lib().b200pose_post_status(self._h, img))
 
@@ -133,6 +140,7 @@ class PoseEngine:
         nat.check(nat.lib().b200pose_infer(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H, W,
                                            self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)), "b200pose_infer")
         self._last = (n, H, W)
+        return self.post.last_ticket()
 
     def infer_async_u8(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
         """uint8 HWC BGR frames [n,H,W,3] (host pinned or device); preprocessing runs on the device."""
@@ -140,10 +148,15 @@ class PoseEngine:
                                               W, self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
                   "b200pose_infer_u8")
         self._last = (n, H, W)
+        return self.post.last_ticket()
 
-    def fetch(self, check=True):
+    def fetch(self, check=True, ticket=None):
+        """Results of run `ticket` (default: the latest).  Up to two runs may be in flight: submit i+1, then fetch i."""
         n, H, W = self._last
-        self.post.sync()
+        if ticket is None:
+            self.post.sync()
+        else:
+            self.post.select(ticket)
         if check:
             self.post.check_status(n)
         return [humans_to_dicts(self.post.humans(i), W, H) for i in range(n)]

@@ -237,3 +237,26 @@ def test_uint8_input_path_fuses_rtpose_preprocess(native_net, he_sd):
     with torch.no_grad():
         _, saved = net_port.forward(he_sd, x)
     assert max(float((o.cpu() - s).abs().max()) for o, s in zip(outs, saved)) < FP32_TOL
+
+
+def test_two_runs_in_flight_results_are_kept_apart(built):
+    """Run i+1 may be submitted before run i is read: results land in parity slots of pinned host memory."""
+    eng, nat = pkg_module("engine"), pkg_module("_native")
+    port = pafprocess_oracle.load_port()
+    maps = [synth.stick_figures(p, s)[:2] for p, s in ((4, 31), (9, 32), (2, 33))]
+    post = eng.NativePost(0, batch_cap=1, peak_cap=256, human_cap=128)
+    tickets = []
+    for hm, pf in maps[:2]:
+        post.run(hm.ctypes.data, pf.ctypes.data, False, 1, 1, 46, 46, 0.1)
+        tickets.append(post.last_ticket())
+    assert tickets == [0, 1]
+    for t, (hm, pf) in zip(tickets, maps[:2]):
+        post.select(t)
+        _, want = glue_port.paf_to_pose(hm, pf, port)
+        assert_humans_equal(eng.humans_to_dicts(post.humans(0), 368, 368), want, score_tol=0.0)
+    post.run(maps[2][0].ctypes.data, maps[2][1].ctypes.data, False, 1, 1, 46, 46, 0.1)
+    with pytest.raises(nat.B200PoseError):
+        post.select(0)                      # overwritten: only the last two runs are retained
+    post.select(2)
+    _, want = glue_port.paf_to_pose(maps[2][0], maps[2][1], port)
+    assert_humans_equal(eng.humans_to_dicts(post.humans(0), 368, 368), want, score_tol=0.0)
