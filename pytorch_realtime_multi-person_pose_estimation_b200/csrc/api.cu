@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -90,6 +91,13 @@ uint16_t f2bf(float f) {
     return (uint16_t)(u >> 16);
 }
 
+float bf2f(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -127,7 +135,11 @@ struct b200pose_net {
     int pn = 0, pH = 0, pW = 0, pmode = -1;
     std::vector<ConvTcArgs> plan;
     std::vector<double> plan_flops;   // algorithmic FLOPs per launch of `plan`
+    bool plan_split = false;          // the plan was built for the split-precision (bf16x3) mode
     DevBuf<__nv_bfloat16> t1, t2, t3, t4, t5a, t5b, t6, t7, t8, t9, cat, bra, brb, br512;
+    // residual ("lo") planes of the same buffers, split-precision mode only
+    DevBuf<__nv_bfloat16> l1, l2, l3, l4, l5a, l5b, l6, l7, l8, l9, lcat, lbra, lbrb, lbr512;
+    std::map<const void*, __nv_bfloat16*> lo_of;
     DevBuf<float> in_stage, out_f32[12];
     // fp32 parity buffers
     DevBuf<float> f_a, f_b, f_cat, f_x, f_y, f_in, f_u8;
@@ -172,7 +184,8 @@ int pack_tc_layer(b200pose_net* net, TcLayer& L, const std::vector<int>& conv_id
     const int taps = ks * ks, rows = groups * cout_pad;
     L.macs_per_pixel = 0;
     for (int g = 0; g < groups; ++g) L.macs_per_pixel += (double)conv_spec(conv_ids[g]).cin * conv_spec(conv_ids[g]).cout * taps;
-    std::vector<uint16_t> w((size_t)taps * rows * cin_pad, 0);
+    // [hi taps | lo taps]: bf16(w) and the residual bf16(w - hi) (used by the split-precision mode only)
+    std::vector<uint16_t> w((size_t)2 * taps * rows * cin_pad, 0);
     std::vector<float> b((size_t)rows, 0.f);
     for (int g = 0; g < groups; ++g) {
         const ConvSpec s = conv_spec(conv_ids[g]);
@@ -182,8 +195,12 @@ int pack_tc_layer(b200pose_net* net, TcLayer& L, const std::vector<int>& conv_id
             b[g * cout_pad + o] = hb[o];
             for (int c = 0; c < s.cin; ++c) {
                 const int pc = cat_input ? cat_phys(c) : c;
-                for (int t = 0; t < taps; ++t)
-                    w[((size_t)t * rows + g * cout_pad + o) * cin_pad + pc] = f2bf(hw[((size_t)o * s.cin + c) * taps + t]);
+                for (int t = 0; t < taps; ++t) {
+                    const float wf = hw[((size_t)o * s.cin + c) * taps + t];
+                    const uint16_t hi = f2bf(wf);
+                    w[((size_t)t * rows + g * cout_pad + o) * cin_pad + pc] = hi;
+                    w[((size_t)(taps + t) * rows + g * cout_pad + o) * cin_pad + pc] = f2bf(wf - bf2f(hi));
+                }
             }
         }
     }
@@ -208,14 +225,20 @@ int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __n
     a.out_f32[0] = f32_0; a.out_f32[1] = f32_1;
     a.f32_ch[0] = f32c0; a.f32_ch[1] = f32c1;
     a.use_base_offset = 0;
-    cudaError_t e = conv_tc_make_maps(a, in, in_cstride, L.w);
+    const __nv_bfloat16* in_lo = nullptr;
+    if (net->plan_split) {
+        a.split = 1;
+        in_lo = net->lo_of.at(in);
+        a.out_lo = net->lo_of.at(out);
+    }
+    cudaError_t e = conv_tc_make_maps(a, in, in_cstride, L.w, in_lo);
     if (e != cudaSuccess) return fail("conv_tc_make_maps failed: %s", cudaGetErrorString(e));
     net->plan.push_back(a);
     net->plan_flops.push_back(2.0 * n * H * W * L.macs_per_pixel);
     return 0;
 }
 
-int build_plan_bf16(b200pose_net* net, int n, int H, int W) {
+int build_plan_bf16(b200pose_net* net, int n, int H, int W, bool split) {
     const size_t px1 = (size_t)n * H * W, px2 = px1 / 4, px4 = px1 / 16, px8 = px1 / 64;
     const int h = H / 8, w = W / 8;
     CU(net->t1.ensure(px1 * 64)); CU(net->t2.ensure(px2 * 64)); CU(net->t3.ensure(px2 * 128));
@@ -224,6 +247,21 @@ int build_plan_bf16(b200pose_net* net, int n, int H, int W) {
     CU(net->t9.ensure(px8 * 256)); CU(net->cat.ensure(px8 * 192)); CU(net->bra.ensure(px8 * 256));
     CU(net->brb.ensure(px8 * 256)); CU(net->br512.ensure(px8 * 1024));
     CU(cudaMemset(net->cat.p, 0, px8 * 192 * 2));
+    net->plan_split = split;
+    net->lo_of.clear();
+    if (split) {
+        CU(net->l1.ensure(px1 * 64)); CU(net->l2.ensure(px2 * 64)); CU(net->l3.ensure(px2 * 128));
+        CU(net->l4.ensure(px4 * 128)); CU(net->l5a.ensure(px4 * 256)); CU(net->l5b.ensure(px4 * 256));
+        CU(net->l6.ensure(px8 * 256)); CU(net->l7.ensure(px8 * 512)); CU(net->l8.ensure(px8 * 512));
+        CU(net->l9.ensure(px8 * 256)); CU(net->lcat.ensure(px8 * 192)); CU(net->lbra.ensure(px8 * 256));
+        CU(net->lbrb.ensure(px8 * 256)); CU(net->lbr512.ensure(px8 * 1024));
+        CU(cudaMemset(net->lcat.p, 0, px8 * 192 * 2));
+        DevBuf<__nv_bfloat16>* hi[] = {&net->t1, &net->t2, &net->t3, &net->t4, &net->t5a, &net->t5b, &net->t6, &net->t7,
+                                       &net->t8, &net->t9, &net->cat, &net->bra, &net->brb, &net->br512};
+        DevBuf<__nv_bfloat16>* lo[] = {&net->l1, &net->l2, &net->l3, &net->l4, &net->l5a, &net->l5b, &net->l6, &net->l7,
+                                       &net->l8, &net->l9, &net->lcat, &net->lbra, &net->lbrb, &net->lbr512};
+        for (int i = 0; i < 14; ++i) net->lo_of[hi[i]->p] = lo[i]->p;
+    }
     for (int i = 0; i < 12; ++i) CU(net->out_f32[i].ensure(px8 * (i % 2 == 0 ? kPaf : kHeat)));
     net->plan.clear();
     net->plan_flops.clear();
@@ -263,13 +301,14 @@ int build_plan_bf16(b200pose_net* net, int n, int H, int W) {
     return 0;
 }
 
-int forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, int W, cudaStream_t st) {
-    if (net->pn != n || net->pH != H || net->pW != W || net->pmode != B200POSE_MODE_BF16) {
+int forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, int W, cudaStream_t st, bool split) {
+    const int want = split ? B200POSE_MODE_BF16X3 : B200POSE_MODE_BF16;
+    if (net->pn != n || net->pH != H || net->pW != W || net->pmode != want) {
         CU(cudaStreamSynchronize(st));
-        if (build_plan_bf16(net, n, H, W)) return 1;
-        net->pn = n; net->pH = H; net->pW = W; net->pmode = B200POSE_MODE_BF16;
+        if (build_plan_bf16(net, n, H, W, split)) return 1;
+        net->pn = n; net->pH = H; net->pW = W; net->pmode = want;
     }
-    CU(conv_first_launch(d_in, in_u8, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st));
+    CU(conv_first_launch(d_in, in_u8, net->d_w[0], net->d_b[0], net->t1.p, split ? net->l1.p : nullptr, n, H, W, st));
     ++g_launches;
     for (const ConvTcArgs& a : net->plan) {
         CU(conv_tc_launch(a, net->num_sms, st));
@@ -385,6 +424,9 @@ void b200pose_net_destroy(b200pose_net* net) {
     DevBuf<__nv_bfloat16>* bb[] = {&net->t1, &net->t2, &net->t3, &net->t4, &net->t5a, &net->t5b, &net->t6,
                                    &net->t7, &net->t8, &net->t9, &net->cat, &net->bra, &net->brb, &net->br512};
     for (auto* b : bb) b->release();
+    DevBuf<__nv_bfloat16>* lb[] = {&net->l1, &net->l2, &net->l3, &net->l4, &net->l5a, &net->l5b, &net->l6,
+                                   &net->l7, &net->l8, &net->l9, &net->lcat, &net->lbra, &net->lbrb, &net->lbr512};
+    for (auto* b : lb) b->release();
     DevBuf<float>* fb[] = {&net->in_stage, &net->f_a, &net->f_b, &net->f_cat, &net->f_x, &net->f_y, &net->f_in, &net->f_u8};
     net->in_stage_u8.release();
     for (auto* b : fb) b->release();
@@ -469,7 +511,7 @@ static int net_forward_impl(b200pose_net* net, const void* input, int in_u8, int
             ++g_launches;
             rc = forward_fp32(net, net->f_u8.p, n, H, W, st);
         } else rc = forward_fp32(net, static_cast<const float*>(d_in), n, H, W, st);
-    } else rc = forward_bf16(net, d_in, in_u8, n, H, W, st);
+    } else rc = forward_bf16(net, d_in, in_u8, n, H, W, st, mode == B200POSE_MODE_BF16X3);
     if (rc) return rc;
     net->last_in = d_in;
     net->last_in_u8 = (mode == B200POSE_MODE_FP32) ? 0 : in_u8;
@@ -498,7 +540,7 @@ int b200pose_net_forward_u8(b200pose_net* net, const unsigned char* images, int 
 }
 
 int b200pose_net_profile(b200pose_net* net, float* ms, double* flops, int cap, void* cuda_stream) {
-    if (!net || net->plan.empty() || net->pmode != B200POSE_MODE_BF16) return -1;
+    if (!net || net->plan.empty() || (net->pmode != B200POSE_MODE_BF16 && net->pmode != B200POSE_MODE_BF16X3)) return -1;
     if (cudaSetDevice(net->device) != cudaSuccess) return -1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     const int n = net->pn, H = net->pH, W = net->pW;
@@ -510,7 +552,8 @@ int b200pose_net_profile(b200pose_net* net, float* ms, double* flops, int cap, v
     DevBuf<float> tmp;
     if (!d_in) { if (tmp.ensure((size_t)n * 3 * H * W) != cudaSuccess) return -1; cudaMemsetAsync(tmp.p, 0, (size_t)n * 3 * H * W * 4, st); d_in = tmp.p; net->last_in_u8 = 0; }
     cudaEventRecord(ev[0], st);
-    conv_first_launch(d_in, net->last_in_u8, net->d_w[0], net->d_b[0], net->t1.p, n, H, W, st);
+    conv_first_launch(d_in, net->last_in_u8, net->d_w[0], net->d_b[0], net->t1.p, net->plan_split ? net->l1.p : nullptr, n, H, W,
+                      st);
     cudaEventRecord(ev[1], st);
     for (size_t i = 0; i < net->plan.size(); ++i) {
         conv_tc_launch(net->plan[i], net->num_sms, st);

@@ -26,7 +26,8 @@ constexpr int kF_Threads = 128;
 template <bool kU8>
 __global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const void* __restrict__ in_v, const float* __restrict__ wgt,
                                                                 const float* __restrict__ bias,
-                                                                __nv_bfloat16* __restrict__ out, int H, int W) {
+                                                                __nv_bfloat16* __restrict__ out,
+                                                                __nv_bfloat16* __restrict__ out_lo, int H, int W) {
     __shared__ float s_in[3][kF_TH + 2][kF_TW + 2];
     __shared__ __align__(16) float s_w[27][64];
     __shared__ float s_b[64];
@@ -109,6 +110,18 @@ __global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const void* __re
                 }
                 reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                if (out_lo != nullptr) {     // split-precision mode: residual plane v - bf16(v)
+                    __nv_bfloat16* dlo = out_lo + (dst - out);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float v0 = fmaxf(acc[p][2 * j], 0.f), v1 = fmaxf(acc[p][2 * j + 1], 0.f);
+                        __nv_bfloat162 b = __floats2bfloat162_rn(v0 - __bfloat162float(__float2bfloat16_rn(v0)),
+                                                                 v1 - __bfloat162float(__float2bfloat16_rn(v1)));
+                        pk[j] = *reinterpret_cast<uint32_t*>(&b);
+                    }
+                    reinterpret_cast<uint4*>(dlo)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    reinterpret_cast<uint4*>(dlo)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
             }
         }
     }
@@ -219,10 +232,10 @@ __global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ in, float* __r
 }  // namespace
 
 cudaError_t conv_first_launch(const void* in, int in_is_u8_hwc, const float* w_oihw, const float* bias,
-                              __nv_bfloat16* out_nhwc, int N, int H, int W, cudaStream_t s) {
+                              __nv_bfloat16* out_nhwc, __nv_bfloat16* out_lo, int N, int H, int W, cudaStream_t s) {
     dim3 grid((W + kF_TW - 1) / kF_TW, (H + kF_TH - 1) / kF_TH, N);
-    if (in_is_u8_hwc) conv_first_kernel<true><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, H, W);
-    else conv_first_kernel<false><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, H, W);
+    if (in_is_u8_hwc) conv_first_kernel<true><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W);
+    else conv_first_kernel<false><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W);
     return cudaGetLastError();
 }
 

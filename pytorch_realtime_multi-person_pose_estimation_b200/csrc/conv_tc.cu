@@ -74,10 +74,12 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
     const int pad = a.ksize >> 1;
     const uint32_t patch_tx = kPatchPitch * (kTileH + a.ksize - 1) * 128;
     const uint32_t b_tx = a.n_tile * 128;
+    const int nterms = a.split ? 3 : 1;   // split mode: A_hi*W_hi, A_hi*W_lo, A_lo*W_hi per K block
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&a.tm_in);
         tma_prefetch_desc(&a.tm_w);
+        if (a.split) tma_prefetch_desc(&a.tm_in_lo);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -111,11 +113,13 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                 const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
                 const int ch0 = a.in_ch_base + tc.g * a.in_ch_group_stride;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
-                    mbar_wait(&patch_empty[pi], pph ^ 1, 1);
-                    mbar_expect_tx(&patch_full[pi], patch_tx);
-                    tma_load_4d(patch_smem + pi * kPatchBytes, &a.tm_in, &patch_full[pi], ch0 + cb * 64, tc.x0 - pad,
-                                tc.y0 - pad, tc.n);
-                    if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; }
+                    for (int plane = 0; plane <= a.split; ++plane) {     // hi plane, then (split mode) the residual plane
+                        mbar_wait(&patch_empty[pi], pph ^ 1, 1);
+                        mbar_expect_tx(&patch_full[pi], patch_tx);
+                        tma_load_4d(patch_smem + pi * kPatchBytes, plane ? &a.tm_in_lo : &a.tm_in, &patch_full[pi],
+                                    ch0 + cb * 64, tc.x0 - pad, tc.y0 - pad, tc.n);
+                        if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; }
+                    }
                 }
             }
         }
@@ -127,11 +131,14 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                 const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
                 const int wrow = (tc.g * a.n_tiles + tc.nt) * a.n_tile;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
-                    for (int tap = 0; tap < taps; ++tap) {
-                        mbar_wait(&b_empty[bi], bph ^ 1, 2);
-                        mbar_expect_tx(&b_full[bi], b_tx);
-                        tma_load_3d(b_smem + bi * kBStageBytes, &a.tm_w, &b_full[bi], cb * 64, wrow, tap);
-                        if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
+                    for (int term = 0; term < nterms; ++term) {          // W_hi, (split) W_lo, W_hi
+                        const int wsel = (term == 1) ? taps : 0;
+                        for (int tap = 0; tap < taps; ++tap) {
+                            mbar_wait(&b_empty[bi], bph ^ 1, 2);
+                            mbar_expect_tx(&b_full[bi], b_tx);
+                            tma_load_3d(b_smem + bi * kBStageBytes, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap);
+                            if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
+                        }
                     }
                 }
             }
@@ -157,35 +164,39 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                 const uint32_t d_tmem = tmem_base + ai * 256;
                 uint32_t accumulate = 0;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
-                    mbar_wait(&patch_full[pi], pph, 4);
-                    uint32_t a_lo = patch_lo0 + pi * (kPatchBytes >> 4);     // window start of tap (0,0), sub-tile 0
-                    int dx = 0;
-                    for (int tap = 0; tap < taps; ++tap) {
-                        mbar_wait(&b_full[bi], bph, 5);
-                        tc_fence_after();
-                        const uint32_t b_lo = b_lo0 + bi * (kBStageBytes >> 4);
-                        if (elect_one()) {
+                    for (int term = 0; term < nterms; ++term) {
+                        // term 0 and 1 read the hi patch (against W_hi, W_lo), term 2 the residual patch (against W_hi)
+                        if (term != 1) mbar_wait(&patch_full[pi], pph, 4);
+                        const bool release_patch = (term == nterms - 1) || (term == 1);
+                        uint32_t a_lo = patch_lo0 + pi * (kPatchBytes >> 4);     // window start of tap (0,0), sub-tile 0
+                        int dx = 0;
+                        for (int tap = 0; tap < taps; ++tap) {
+                            mbar_wait(&b_full[bi], bph, 5);
+                            tc_fence_after();
+                            const uint32_t b_lo = b_lo0 + bi * (kBStageBytes >> 4);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int sub = 0; sub < 2; ++sub) {
+                                for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    umma_bf16(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
-                                              bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
+                                    for (int k = 0; k < 4; ++k) {
+                                        umma_bf16(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
+                                                  bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
+                                    }
+                                }
+                                umma_commit(&b_empty[bi]);
+                                if (tap == taps - 1) {
+                                    if (release_patch) umma_commit(&patch_empty[pi]);
+                                    if (cb == a.cin_blocks - 1 && term == nterms - 1) umma_commit(&acc_full[ai]);
                                 }
                             }
-                            umma_commit(&b_empty[bi]);
-                            if (tap == taps - 1) {
-                                umma_commit(&patch_empty[pi]);
-                                if (cb == a.cin_blocks - 1) umma_commit(&acc_full[ai]);
-                            }
+                            __syncwarp();
+                            accumulate = 1;
+                            if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
+                            a_lo += 8;                                            // next tap: one pixel (128 B) to the right
+                            if (++dx == a.ksize) { dx = 0; a_lo += row_wrap; }
                         }
-                        __syncwarp();
-                        accumulate = 1;
-                        if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
-                        a_lo += 8;                                            // next tap: one pixel (128 B) to the right
-                        if (++dx == a.ksize) { dx = 0; a_lo += row_wrap; }
+                        if (release_patch) { if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; } }
                     }
-                    if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; }
                 }
                 if (++ai == 2) { ai = 0; aph ^= 1; }
             }
@@ -265,6 +276,21 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                                     *reinterpret_cast<uint4*>(dst + 8 * q8) = u;
                                 }
                             }
+                            if (a.out_lo != nullptr) {      // split mode: residual plane v - bf16(v)
+                                __nv_bfloat16* dlo = a.out_lo + (dst - a.out);
+#pragma unroll
+                                for (int q8 = 0; q8 < 4; ++q8) {
+                                    if (c0 + 8 * q8 < store_ch) {
+                                        float r8[8];
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j)
+                                            r8[j] = v[8 * q8 + j] - __bfloat162float(__float2bfloat16_rn(v[8 * q8 + j]));
+                                        uint4 u = make_uint4(pack_bf16x2(r8[0], r8[1]), pack_bf16x2(r8[2], r8[3]),
+                                                             pack_bf16x2(r8[4], r8[5]), pack_bf16x2(r8[6], r8[7]));
+                                        *reinterpret_cast<uint4*>(dlo + 8 * q8) = u;
+                                    }
+                                }
+                            }
                         }
                         if (of32 != nullptr) {
 #pragma unroll
@@ -311,19 +337,22 @@ PFN_encodeTiled get_encode_fn() {
 
 }  // namespace
 
-cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cstride, const __nv_bfloat16* w) {
+cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cstride, const __nv_bfloat16* w,
+                              const __nv_bfloat16* in_lo) {
     PFN_encodeTiled enc = get_encode_fn();
     if (enc == nullptr) return cudaErrorNotSupported;
     if (a.ksize != 1 && a.ksize != 3 && a.ksize != 7) return cudaErrorInvalidValue;
     if (a.n_tile % 16 != 0 || a.n_tile < 16 || a.n_tile > 128) return cudaErrorInvalidValue;
     if (a.groups < 1 || a.groups > 2 || in_cstride % 8 != 0) return cudaErrorInvalidValue;
-    {
+    if (a.split && in_lo == nullptr) return cudaErrorInvalidValue;
+    for (int plane = 0; plane <= (a.split ? 1 : 0); ++plane) {
         cuuint64_t dims[4] = {(cuuint64_t)in_cstride, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n_img};
         cuuint64_t strides[3] = {(cuuint64_t)in_cstride * 2, (cuuint64_t)a.W * in_cstride * 2,
                                  (cuuint64_t)a.H * a.W * in_cstride * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)kPatchPitch, (cuuint32_t)(kTileH + a.ksize - 1), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&a.tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(in), dims, strides,
+        CUresult r = enc(plane ? &a.tm_in_lo : &a.tm_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                         const_cast<__nv_bfloat16*>(plane ? in_lo : in), dims, strides,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -335,7 +364,7 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
         const int cin_pad = a.cin_blocks * 64;
         const int rows = a.groups * a.n_tiles * a.n_tile;
         const int taps = a.ksize * a.ksize;
-        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)rows, (cuuint64_t)taps};
+        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)rows, (cuuint64_t)(2 * taps)};
         cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)rows * cin_pad * 2};
         cuuint32_t box[3] = {64, (cuuint32_t)a.n_tile, 1};
         cuuint32_t estr[3] = {1, 1, 1};
