@@ -98,6 +98,27 @@ float bf2f(uint16_t b) {
     return f;
 }
 
+// float -> IEEE half bits, round to nearest even (normals, subnormals, overflow to inf)
+uint16_t f2h(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0));
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                 // rounds to >= 65520 -> inf
+    if (x < 0x33000001u) return (uint16_t)sign;                              // < 2^-25: rounds to zero
+    int e = (int)(x >> 23) - 127;
+    uint32_t m = (x & 0x7fffffu) | 0x800000u;
+    int shift;
+    uint32_t base;
+    if (e < -14) { shift = 13 + (-14 - e); base = 0; }                       // subnormal half
+    else { shift = 13; base = (uint32_t)(e + 15) << 10; m &= 0x7fffffu; }
+    const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    uint32_t h = base + q;
+    if (rem > half || (rem == half && (h & 1u))) h += 1;
+    return (uint16_t)(sign | h);
+}
+
 template <class T> struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
@@ -184,7 +205,7 @@ int pack_tc_layer(b200pose_net* net, TcLayer& L, const std::vector<int>& conv_id
     const int taps = ks * ks, rows = groups * cout_pad;
     L.macs_per_pixel = 0;
     for (int g = 0; g < groups; ++g) L.macs_per_pixel += (double)conv_spec(conv_ids[g]).cin * conv_spec(conv_ids[g]).cout * taps;
-    // [hi taps | lo taps]: bf16(w) and the residual bf16(w - hi) (used by the split-precision mode only)
+    // [hi taps | lo taps]: bf16(w) and the residual (w - hi) as FP16 bits (used by the split-precision mode only)
     std::vector<uint16_t> w((size_t)2 * taps * rows * cin_pad, 0);
     std::vector<float> b((size_t)rows, 0.f);
     for (int g = 0; g < groups; ++g) {
@@ -199,7 +220,7 @@ int pack_tc_layer(b200pose_net* net, TcLayer& L, const std::vector<int>& conv_id
                     const float wf = hw[((size_t)o * s.cin + c) * taps + t];
                     const uint16_t hi = f2bf(wf);
                     w[((size_t)t * rows + g * cout_pad + o) * cin_pad + pc] = hi;
-                    w[((size_t)(taps + t) * rows + g * cout_pad + o) * cin_pad + pc] = f2bf(wf - bf2f(hi));
+                    w[((size_t)(taps + t) * rows + g * cout_pad + o) * cin_pad + pc] = f2h(wf - bf2f(hi));   // fp16 residual
                 }
             }
         }

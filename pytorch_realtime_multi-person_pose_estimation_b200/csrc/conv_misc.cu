@@ -9,6 +9,7 @@
 //   nchw_to_nhwc / nhwc_slice_to_nchw : layout glue for the parity path.
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "conv_misc.cuh"
@@ -115,8 +116,8 @@ __global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const void* __re
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float v0 = fmaxf(acc[p][2 * j], 0.f), v1 = fmaxf(acc[p][2 * j + 1], 0.f);
-                        __nv_bfloat162 b = __floats2bfloat162_rn(v0 - __bfloat162float(__float2bfloat16_rn(v0)),
-                                                                 v1 - __bfloat162float(__float2bfloat16_rn(v1)));
+                        __half2 b = __floats2half2_rn(v0 - __bfloat162float(__float2bfloat16_rn(v0)),
+                                                      v1 - __bfloat162float(__float2bfloat16_rn(v1)));   // fp16 residual
                         pk[j] = *reinterpret_cast<uint32_t*>(&b);
                     }
                     reinterpret_cast<uint4*>(dlo)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);

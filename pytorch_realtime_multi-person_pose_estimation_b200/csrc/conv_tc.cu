@@ -20,6 +20,8 @@
 //   * Persistent grid (one CTA per SM), static round-robin tile schedule.
 #include <cstdio>
 
+#include <cuda_fp16.h>
+
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
@@ -42,6 +44,11 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int groups,
     c.y0 = (t % tiles_y) * kTileH;
     c.n = t / tiles_y;
     return c;
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -149,7 +156,10 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
         // elected lane issues the tcgen05 instructions.  A divergent `if (lane == 0)` around the loop makes ptxas wrap
         // every UTCHMMA in an ELECT/BRA.U.ANY uniformisation loop (~2x the issue cost).
         {
-            const uint32_t idesc = make_idesc_bf16_m128(a.n_tile);
+            // split mode: hi planes are bf16, residual planes fp16 (11-bit mantissa: hi + lo carries ~19 bits); the A / B
+            // formats of kind::f16 are independent fields of the instruction descriptor
+            const uint32_t idesc_t[3] = {make_idesc_m128(a.n_tile, 1, 1), make_idesc_m128(a.n_tile, 1, 0),
+                                         make_idesc_m128(a.n_tile, 0, 1)};
             // Descriptors are built incrementally: the high words are loop invariants, the low word (address >> 4)
             // only receives small adds per tap / sub-tile / K step.
             const uint64_t adesc_hi = make_sdesc_sw128(0, kPatchPitch * 128, 0);
@@ -168,6 +178,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                         // term 0 and 1 read the hi patch (against W_hi, W_lo), term 2 the residual patch (against W_hi)
                         if (term != 1) mbar_wait(&patch_full[pi], pph, 4);
                         const bool release_patch = (term == nterms - 1) || (term == 1);
+                        const uint32_t idesc = idesc_t[term];
                         uint32_t a_lo = patch_lo0 + pi * (kPatchBytes >> 4);     // window start of tap (0,0), sub-tile 0
                         int dx = 0;
                         for (int tap = 0; tap < taps; ++tap) {
@@ -285,8 +296,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
 #pragma unroll
                                         for (int j = 0; j < 8; ++j)
                                             r8[j] = v[8 * q8 + j] - __bfloat162float(__float2bfloat16_rn(v[8 * q8 + j]));
-                                        uint4 u = make_uint4(pack_bf16x2(r8[0], r8[1]), pack_bf16x2(r8[2], r8[3]),
-                                                             pack_bf16x2(r8[4], r8[5]), pack_bf16x2(r8[6], r8[7]));
+                                        uint4 u = make_uint4(pack_f16x2(r8[0], r8[1]), pack_f16x2(r8[2], r8[3]),
+                                                             pack_f16x2(r8[4], r8[5]), pack_f16x2(r8[6], r8[7]));
                                         *reinterpret_cast<uint4*>(dlo + 8 * q8) = u;
                                     }
                                 }
