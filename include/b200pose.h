@@ -30,8 +30,10 @@ typedef struct b200pose_net b200pose_net;
 #define B200POSE_NUM_TENSORS 184   /* state_dict entries, reference order (model0, model{1..6}_1, model{1..6}_2) */
 #define B200POSE_MODE_BF16 0       /* tcgen05 tensor cores, bf16 operands, fp32 accumulate                       */
 #define B200POSE_MODE_FP32 1       /* fp32-parity mode: fp32 FMA everywhere (1e-3 bar of BASELINE.json)          */
-#define B200POSE_MODE_BF16X3 2     /* tensor-core parity mode ("f16x3"): FP16 value + FP16 residual planes for activations
-                                      and weights (22 mantissa bits), 3 MMA terms per K block, fp32 accumulate        */
+#define B200POSE_MODE_BF16X3 2     /* high-precision tensor-core mode: value + residual bf16 planes for activations and
+                                      weights, 3 MMA terms per K block (A_hi*W_hi + A_hi*W_lo + A_lo*W_hi); measured
+                                      1.4e-3 max-abs @368x368 (bf16: 7e-2, fp32 mode: 3e-5) - the tensor core's own fp32
+                                      accumulation is the floor, see DESIGN.md 2.3                                   */
 
 int b200pose_net_create(b200pose_net** out, int cuda_device);
 void b200pose_net_destroy(b200pose_net* net);

@@ -10,7 +10,7 @@ c_float_p = ctypes.POINTER(ctypes.c_float)
 NUM_TENSORS = 184
 HUMAN_FLOATS = 73
 MODE_BF16, MODE_FP32, MODE_BF16X3 = 0, 1, 2
-MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "f16x3": MODE_BF16X3, "bf16x3": MODE_BF16X3}
+MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "bf16x3": MODE_BF16X3}
 
 
 class B200PoseError(RuntimeError):

@@ -91,50 +91,11 @@ uint16_t f2bf(float f) {
     return (uint16_t)(u >> 16);
 }
 
-float h2f(uint16_t h) {   // IEEE half bits -> float
-    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
-    uint32_t x;
-    if (e == 0) {
-        if (m == 0) x = sign;
-        else {
-            int sh = 0;
-            uint32_t mm = m;
-            while (!(mm & 0x400u)) { mm <<= 1; ++sh; }
-            x = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | ((mm & 0x3ffu) << 13);
-        }
-    } else if (e == 31) x = sign | 0x7f800000u | (m << 13);
-    else x = sign | ((e + 112) << 23) | (m << 13);
-    float f;
-    memcpy(&f, &x, 4);
-    return f;
-}
-
 float bf2f(uint16_t b) {
     uint32_t u = (uint32_t)b << 16;
     float f;
     memcpy(&f, &u, 4);
     return f;
-}
-
-// float -> IEEE half bits, round to nearest even (normals, subnormals, overflow to inf)
-uint16_t f2h(float f) {
-    uint32_t x;
-    memcpy(&x, &f, 4);
-    const uint32_t sign = (x >> 16) & 0x8000u;
-    x &= 0x7fffffffu;
-    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0));
-    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                 // rounds to >= 65520 -> inf
-    if (x < 0x33000001u) return (uint16_t)sign;                              // < 2^-25: rounds to zero
-    int e = (int)(x >> 23) - 127;
-    uint32_t m = (x & 0x7fffffu) | 0x800000u;
-    int shift;
-    uint32_t base;
-    if (e < -14) { shift = 13 + (-14 - e); base = 0; }                       // subnormal half
-    else { shift = 13; base = (uint32_t)(e + 15) << 10; m &= 0x7fffffu; }
-    const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
-    uint32_t h = base + q;
-    if (rem > half || (rem == half && (h & 1u))) h += 1;
-    return (uint16_t)(sign | h);
 }
 
 template <class T> struct DevBuf {
@@ -223,8 +184,8 @@ int pack_tc_layer(b200pose_net* net, TcLayer& L, const std::vector<int>& conv_id
     const int taps = ks * ks, rows = groups * cout_pad;
     L.macs_per_pixel = 0;
     for (int g = 0; g < groups; ++g) L.macs_per_pixel += (double)conv_spec(conv_ids[g]).cin * conv_spec(conv_ids[g]).cout * taps;
-    // three sections of `taps` slices: bf16(w) (bf16 mode); half(w) and the residual half(w - half(w)) (split mode)
-    std::vector<uint16_t> w((size_t)3 * taps * rows * cin_pad, 0);
+    // [hi taps | lo taps]: bf16(w) and the residual bf16(w - hi) (used by the split-precision mode only)
+    std::vector<uint16_t> w((size_t)2 * taps * rows * cin_pad, 0);
     std::vector<float> b((size_t)rows, 0.f);
     for (int g = 0; g < groups; ++g) {
         const ConvSpec s = conv_spec(conv_ids[g]);
@@ -236,10 +197,9 @@ int pack_tc_layer(b200pose_net* net, TcLayer& L, const std::vector<int>& conv_id
                 const int pc = cat_input ? cat_phys(c) : c;
                 for (int t = 0; t < taps; ++t) {
                     const float wf = hw[((size_t)o * s.cin + c) * taps + t];
-                    const uint16_t h16 = f2h(wf);
-                    w[((size_t)t * rows + g * cout_pad + o) * cin_pad + pc] = f2bf(wf);
-                    w[((size_t)(taps + t) * rows + g * cout_pad + o) * cin_pad + pc] = h16;
-                    w[((size_t)(2 * taps + t) * rows + g * cout_pad + o) * cin_pad + pc] = f2h(wf - h2f(h16));
+                    const uint16_t hi = f2bf(wf);
+                    w[((size_t)t * rows + g * cout_pad + o) * cin_pad + pc] = hi;
+                    w[((size_t)(taps + t) * rows + g * cout_pad + o) * cin_pad + pc] = f2bf(wf - bf2f(hi));
                 }
             }
         }

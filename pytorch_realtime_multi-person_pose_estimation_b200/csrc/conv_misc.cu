@@ -9,7 +9,6 @@
 //   nchw_to_nhwc / nhwc_slice_to_nchw : layout glue for the parity path.
 #include <cstdint>
 #include <cuda_bf16.h>
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "conv_misc.cuh"
@@ -109,24 +108,19 @@ __global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const void* __re
                     __nv_bfloat162 b = __floats2bfloat162_rn(fmaxf(acc[p][2 * j], 0.f), fmaxf(acc[p][2 * j + 1], 0.f));
                     pk[j] = *reinterpret_cast<uint32_t*>(&b);
                 }
-                if (out_lo != nullptr) {     // split-precision mode: FP16 value plane + FP16 residual plane
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                if (out_lo != nullptr) {     // split-precision mode: residual plane v - bf16(v)
                     __nv_bfloat16* dlo = out_lo + (dst - out);
-                    uint32_t ph[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float v0 = fmaxf(acc[p][2 * j], 0.f), v1 = fmaxf(acc[p][2 * j + 1], 0.f);
-                        __half2 hv = __floats2half2_rn(v0, v1);
-                        __half2 lv = __floats2half2_rn(v0 - __low2float(hv), v1 - __high2float(hv));
-                        ph[j] = *reinterpret_cast<uint32_t*>(&hv);
-                        pk[j] = *reinterpret_cast<uint32_t*>(&lv);
+                        __nv_bfloat162 b = __floats2bfloat162_rn(v0 - __bfloat162float(__float2bfloat16_rn(v0)),
+                                                                 v1 - __bfloat162float(__float2bfloat16_rn(v1)));
+                        pk[j] = *reinterpret_cast<uint32_t*>(&b);
                     }
-                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
                     reinterpret_cast<uint4*>(dlo)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     reinterpret_cast<uint4*>(dlo)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                } else {
-                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
             }
         }

@@ -20,8 +20,6 @@
 //   * Persistent grid (one CTA per SM), static round-robin tile schedule.
 #include <cstdio>
 
-#include <cuda_fp16.h>
-
 #include "conv_tc.cuh"
 #include "ptx.cuh"
 
@@ -44,11 +42,6 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int groups,
     c.y0 = (t % tiles_y) * kTileH;
     c.n = t / tiles_y;
     return c;
-}
-
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -139,8 +132,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                 const int wrow = (tc.g * a.n_tiles + tc.nt) * a.n_tile;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
                     for (int term = 0; term < nterms; ++term) {          // W_hi, (split) W_lo, W_hi
-                        // weight tensor sections: [bf16 | f16 hi | f16 residual] x taps
-                        const int wsel = a.split ? (term == 1 ? 2 * taps : taps) : 0;
+                        const int wsel = (term == 1) ? taps : 0;
                         for (int tap = 0; tap < taps; ++tap) {
                             mbar_wait(&b_empty[bi], bph ^ 1, 2);
                             mbar_expect_tx(&b_full[bi], b_tx);
@@ -157,9 +149,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
         // elected lane issues the tcgen05 instructions.  A divergent `if (lane == 0)` around the loop makes ptxas wrap
         // every UTCHMMA in an ELECT/BRA.U.ANY uniformisation loop (~2x the issue cost).
         {
-            // split mode: every plane (hi and residual, activations and weights) is FP16, so hi + lo carries 22 mantissa
-            // bits and all three terms are f16 x f16 MMAs (mixed bf16 x f16 operands trap as an illegal instruction)
-            const uint32_t idesc = a.split ? make_idesc_m128(a.n_tile, 0, 0) : make_idesc_bf16_m128(a.n_tile);
+            const uint32_t idesc = make_idesc_bf16_m128(a.n_tile);
             // Descriptors are built incrementally: the high words are loop invariants, the low word (address >> 4)
             // only receives small adds per tap / sub-tile / K step.
             const uint64_t adesc_hi = make_sdesc_sw128(0, kPatchPitch * 128, 0);
@@ -278,16 +268,15 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                         if (a.out != nullptr) {
                             __nv_bfloat16* dst = a.out + (static_cast<size_t>(tc.n * Ho + yo) * Wo + xo) * a.out_cstride +
                                                  a.out_ch_off[tc.g] + ch_tile + c0;
-                            if (a.out_lo == nullptr) {
 #pragma unroll
-                                for (int q8 = 0; q8 < 4; ++q8) {
-                                    if (c0 + 8 * q8 < store_ch) {
-                                        uint4 u = make_uint4(pack_bf16x2(v[8 * q8], v[8 * q8 + 1]), pack_bf16x2(v[8 * q8 + 2], v[8 * q8 + 3]),
-                                                             pack_bf16x2(v[8 * q8 + 4], v[8 * q8 + 5]), pack_bf16x2(v[8 * q8 + 6], v[8 * q8 + 7]));
-                                        *reinterpret_cast<uint4*>(dst + 8 * q8) = u;
-                                    }
+                            for (int q8 = 0; q8 < 4; ++q8) {
+                                if (c0 + 8 * q8 < store_ch) {
+                                    uint4 u = make_uint4(pack_bf16x2(v[8 * q8], v[8 * q8 + 1]), pack_bf16x2(v[8 * q8 + 2], v[8 * q8 + 3]),
+                                                         pack_bf16x2(v[8 * q8 + 4], v[8 * q8 + 5]), pack_bf16x2(v[8 * q8 + 6], v[8 * q8 + 7]));
+                                    *reinterpret_cast<uint4*>(dst + 8 * q8) = u;
                                 }
-                            } else {      // split mode: FP16 value plane + FP16 residual plane (v - half(v))
+                            }
+                            if (a.out_lo != nullptr) {      // split mode: residual plane v - bf16(v)
                                 __nv_bfloat16* dlo = a.out_lo + (dst - a.out);
 #pragma unroll
                                 for (int q8 = 0; q8 < 4; ++q8) {
@@ -295,13 +284,10 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                                         float r8[8];
 #pragma unroll
                                         for (int j = 0; j < 8; ++j)
-                                            r8[j] = v[8 * q8 + j] - __half2float(__float2half_rn(v[8 * q8 + j]));
-                                        *reinterpret_cast<uint4*>(dst + 8 * q8) =
-                                            make_uint4(pack_f16x2(v[8 * q8], v[8 * q8 + 1]), pack_f16x2(v[8 * q8 + 2], v[8 * q8 + 3]),
-                                                       pack_f16x2(v[8 * q8 + 4], v[8 * q8 + 5]), pack_f16x2(v[8 * q8 + 6], v[8 * q8 + 7]));
-                                        *reinterpret_cast<uint4*>(dlo + 8 * q8) =
-                                            make_uint4(pack_f16x2(r8[0], r8[1]), pack_f16x2(r8[2], r8[3]),
-                                                       pack_f16x2(r8[4], r8[5]), pack_f16x2(r8[6], r8[7]));
+                                            r8[j] = v[8 * q8 + j] - __bfloat162float(__float2bfloat16_rn(v[8 * q8 + j]));
+                                        uint4 u = make_uint4(pack_bf16x2(r8[0], r8[1]), pack_bf16x2(r8[2], r8[3]),
+                                                             pack_bf16x2(r8[4], r8[5]), pack_bf16x2(r8[6], r8[7]));
+                                        *reinterpret_cast<uint4*>(dlo + 8 * q8) = u;
                                     }
                                 }
                             }
@@ -378,7 +364,7 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
         const int cin_pad = a.cin_blocks * 64;
         const int rows = a.groups * a.n_tiles * a.n_tile;
         const int taps = a.ksize * a.ksize;
-        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)rows, (cuuint64_t)(3 * taps)};
+        cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)rows, (cuuint64_t)(2 * taps)};
         cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)rows * cin_pad * 2};
         cuuint32_t box[3] = {64, (cuuint32_t)a.n_tile, 1};
         cuuint32_t estr[3] = {1, 1, 1};

@@ -42,17 +42,17 @@ struct ConvTcArgs {
     int f32_ch[2];            // valid channels of the fp32 copy
     int use_base_offset;      // descriptor swizzle-phase field
     // ---- split-precision ("bf16x3") mode: operands are hi + lo bf16 planes, three MMA terms per K block
-    int split;                // 0: plain bf16; 1: FP16 hi/lo planes, A_hi*W_hi + A_hi*W_lo + A_lo*W_hi
+    int split;                // 0: plain bf16; 1: A_hi*W_hi + A_hi*W_lo + A_lo*W_hi
     __nv_bfloat16* out_lo;    // residual plane of the output (same geometry as `out`), split mode only
     // ---- tensor maps
     CUtensorMap tm_in;        // 4D (C, W, H, N) bf16, box (64, 24, 16+ks-1, 1), SWIZZLE_128B
-    CUtensorMap tm_w;         // 3D (cin_pad, groups*n_tiles*n_tile, 3*taps) 16-bit [bf16 | f16 hi | f16 residual], box (64, n_tile, 1)
+    CUtensorMap tm_w;         // 3D (cin_pad, groups*n_tiles*n_tile, 2*taps) bf16 [hi taps | lo taps], box (64, n_tile, 1)
     CUtensorMap tm_in_lo;     // residual plane of the input (split mode)
 };
 
 // Builds the tensor maps. `in` (and `in_lo` in split mode): NHWC buffers with `in_cstride` channels per pixel.
-// `w`: packed weights [3*taps][groups*n_tiles*n_tile][cin_blocks*64]: bf16(w) for the first `taps` slices (bf16 mode),
-// then half(w) and the residual half(w - half(w)) (split mode, all-FP16 operands).
+// `w`: packed weights [2*taps][groups*n_tiles*n_tile][cin_blocks*64]: bf16(w) for the first `taps` slices, the
+// residual bf16(w - hi) for the second.
 cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cstride, const __nv_bfloat16* w,
                               const __nv_bfloat16* in_lo = nullptr);
 cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream);

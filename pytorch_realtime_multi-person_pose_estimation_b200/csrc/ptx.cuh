@@ -140,10 +140,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32, both operands K-major, M=128.
 // Bit layout (cf. PTX ISA "Instruction descriptor"): [4,6) D fmt (1=F32), [7,10) A fmt (1=BF16),
 // [10,13) B fmt, [15] A major, [16] B major (0 = K), [17,23) N>>3, [24,29) M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_m128(uint32_t n, uint32_t a_fmt, uint32_t b_fmt) {   // fmt: 0 = F16, 1 = BF16
-    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16_m128(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
-__host__ __device__ constexpr uint32_t make_idesc_bf16_m128(uint32_t n) { return make_idesc_m128(n, 1, 1); }
 
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows are 128 B (64 bf16) apart inside an
 // 8-row group, groups are `sbo_bytes` apart. [0,14) addr>>4, [16,30) LBO>>4 (unused for SW128 K-major),
