@@ -55,7 +55,8 @@ static int run_case(const Case& c, int use_bo, int num_sms) {
                     for (int k = 0; k < c.cin_g; ++k) w[((size_t)t * rows + g * c.cout_g + r) * c.cin_g + k] = 0.f;
             }
 
-    std::vector<__nv_bfloat16> in_h(in.size()), w_h(w.size());
+    // the weight tensor map spans 2*taps slices (value + residual planes); only the first `taps` are used here
+    std::vector<__nv_bfloat16> in_h(in.size()), w_h(2 * w.size(), __float2bfloat16(0.f));
     for (size_t i = 0; i < in.size(); ++i) in_h[i] = __float2bfloat16(in[i]);
     for (size_t i = 0; i < w.size(); ++i) w_h[i] = __float2bfloat16(w[i]);
 
@@ -185,7 +186,7 @@ static void perf(int num_sms, int use_bo) {
         const int Ho = p.pool ? p.H / 2 : p.H, Wo = p.pool ? p.W / 2 : p.W;
         __nv_bfloat16 *d_in, *d_w, *d_out;
         float* d_bias;
-        size_t in_b = (size_t)p.n * p.H * p.W * in_c * 2, w_b = (size_t)taps * rows * p.cin_g * 2;
+        size_t in_b = (size_t)p.n * p.H * p.W * in_c * 2, w_b = (size_t)2 * taps * rows * p.cin_g * 2;
         size_t out_b = (size_t)p.n * Ho * Wo * rows * 2;
         CK(cudaMalloc(&d_in, in_b)); CK(cudaMalloc(&d_w, w_b)); CK(cudaMalloc(&d_out, out_b));
         CK(cudaMalloc(&d_bias, rows * 4));

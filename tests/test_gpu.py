@@ -261,3 +261,13 @@ def test_two_runs_in_flight_results_are_kept_apart(built):
     post.select(2)
     _, want = glue_port.paf_to_pose(maps[2][0], maps[2][1], port)
     assert_humans_equal(eng.humans_to_dicts(post.humans(0), 368, 368), want, score_tol=0.0)
+
+
+def test_picture_demo_script_runs(built, tmp_path):
+    """demo/picture_demo.py: the reference demo's flow (get_model, DataParallel, get_outputs, paf_to_pose_cpp,
+    draw_humans, imwrite) on the B200 path, from the repo root like the reference expects."""
+    out = tmp_path / "result.png"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "demo", "picture_demo.py"), "--precision", "fp32", "--out", str(out)],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0 and out.exists() and "humans" in r.stdout
