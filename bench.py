@@ -92,6 +92,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL's version banner goes there)
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1")
