@@ -497,7 +497,22 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     __shared__ int scan_scratch[kLimbThreads / 32 + 1];
     __shared__ long s_pool_base;
     __shared__ SortShared s_sort;
-    const int limb = blockIdx.x, img = blockIdx.y, tid = threadIdx.x;
+    // Longest-job-first: grid = (image, rank); block `rank` of an image takes the limb with the rank-th largest number
+    // of (a, b) pairs, so across the whole grid the heavy limbs are scheduled before the light ones (shorter tail).
+    const int img = blockIdx.x, tid = threadIdx.x;
+    int limb = blockIdx.y;
+    {
+        int my_pairs[kNumLimb];
+#pragma unroll
+        for (int l = 0; l < kNumLimb; ++l)
+            my_pairs[l] = pb.counts[img * kNumPart + c_limb_parts[l][0]] * pb.counts[img * kNumPart + c_limb_parts[l][1]];
+        for (int l = 0; l < kNumLimb; ++l) {
+            int rank = 0;
+            for (int m = 0; m < kNumLimb; ++m)
+                rank += (my_pairs[m] > my_pairs[l]) || (my_pairs[m] == my_pairs[l] && m < l);
+            if (rank == (int)blockIdx.y) limb = l;
+        }
+    }
     const int pa = c_limb_parts[limb][0], pbp = c_limb_parts[limb][1];
     const int cap = pb.peak_cap;
     const int na = pb.counts[img * kNumPart + pa], nb = pb.counts[img * kNumPart + pbp];
@@ -813,7 +828,7 @@ cudaError_t post_limbs(const PostBuffers& pb, int batch, const float* paf, long 
         B2P_TRY(cudaFuncSetAttribute(limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    limbs_kernel<<<dim3(kNumLimb, batch), kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem);
+    limbs_kernel<<<dim3(batch, kNumLimb), kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem);
     return cudaGetLastError();
 }
 
