@@ -201,6 +201,58 @@ B2P_HD void seq_std_sort(uint64_t* v, int n) {
         seq_insertion_sort(v, 0, n);
 }
 
+// Sequential exact introsort of the sub-range v[first, last) with depth budget `depth` (= what the recursive
+// __introsort_loop call on that range does, followed by the part of __final_insertion_sort that falls into it).
+// One thread; the device runs 32 of these side by side, one small range per lane.
+B2P_HD void seq_sort_range(uint64_t* v, long first, long last, int depth) {
+    long sf[24], sl[24];
+    int sd[24], sp = 1;
+    sf[0] = first; sl[0] = last; sd[0] = depth;
+    while (sp > 0) {
+        --sp;
+        long f = sf[sp], l = sl[sp];
+        int d = sd[sp];
+        bool heap_sorted = false;
+        while (l - f > 16) {
+            if (d == 0) { seq_heap_sort(v, f, l); heap_sorted = true; break; }
+            --d;
+            const long a = f + 1, b = f + (l - f) / 2, c = l - 1;
+            long m;
+            if (B2P_COMP(v[a], v[b])) m = B2P_COMP(v[b], v[c]) ? b : (B2P_COMP(v[a], v[c]) ? c : a);
+            else m = B2P_COMP(v[a], v[c]) ? a : (B2P_COMP(v[b], v[c]) ? c : b);
+            { const uint64_t t = v[f]; v[f] = v[m]; v[m] = t; }
+            const uint32_t pivot = (uint32_t)(v[f] >> 32);
+            long lo = f + 1, hi = l;
+            for (;;) {
+                while ((uint32_t)(v[lo] >> 32) < pivot) ++lo;
+                --hi;
+                while (pivot < (uint32_t)(v[hi] >> 32)) --hi;
+                if (!(lo < hi)) break;
+                const uint64_t t = v[lo]; v[lo] = v[hi]; v[hi] = t;
+                ++lo;
+            }
+            if (l - lo > 16 && sp < 24) { sf[sp] = lo; sl[sp] = l; sd[sp] = d; ++sp; }
+            else if (l - lo > 1) {
+                if (l - lo > 16) seq_std_sort(v + lo, (int)(l - lo));   // stack exhausted: unreachable for ranges <= 2^24
+                else for (long i = lo + 1; i < l; ++i) {                 // leaf: stable insertion sort
+                    const uint64_t val = v[i];
+                    long j = i;
+                    while (j > lo && B2P_COMP(val, v[j - 1])) { v[j] = v[j - 1]; --j; }
+                    v[j] = val;
+                }
+            }
+            l = lo;
+        }
+        if (!heap_sorted)
+            for (long i = f + 1; i < l; ++i) {
+                const uint64_t val = v[i];
+                long j = i;
+                while (j > f && B2P_COMP(val, v[j - 1])) { v[j] = v[j - 1]; --j; }
+                v[j] = val;
+            }
+    }
+}
+
 // ---------------------------------------------------------------- warp-parallel exact std::sort
 // One partition step of libstdc++'s introsort (__unguarded_partition_pivot: median-of-3 of first+1 / mid / last-1
 // moved to `first`, then the Hoare loop `while (comp(*lo, pivot)) ++lo; --hi; while (comp(pivot, *hi)) --hi;
@@ -390,55 +442,64 @@ B2P_HD void bp_count(const BlockPartState& st, const uint64_t* v, int tid, int* 
     }
     *cA = a; *cB = b;
 }
-// offA: lo-stops before this slice; b_right: hi-stops after this slice.  posA/posB are 1-based rank -> position.
-B2P_HD void bp_scatter(const BlockPartState& st, const uint64_t* v, int tid, int offA, int b_right, int32_t* posA,
-                       int32_t* posB) {
+// offA: lo-stops before this slice; b_right: hi-stops after this slice.  posA/posB are 1-based rank -> position
+// tables; positions are stored relative to st.first in PosT (int32 for global-memory ranges, uint16 for the
+// shared-memory ranges of <= 65535 keys).
+template <class PosT>
+B2P_HD void bp_scatter(const BlockPartState& st, const uint64_t* v, int tid, int offA, int b_right, PosT* posA,
+                       PosT* posB) {
     long s, e;
     bp_slice(st, tid, &s, &e);
+    const long f = st.first;
     int a = offA;
     long p = s;
     for (; p + 4 <= e; p += 4) {
         const uint32_t k0 = (uint32_t)(v[p] >> 32), k1 = (uint32_t)(v[p + 1] >> 32);
         const uint32_t k2 = (uint32_t)(v[p + 2] >> 32), k3 = (uint32_t)(v[p + 3] >> 32);
-        if (k0 >= st.pivot) posA[++a] = (int32_t)p;
-        if (k1 >= st.pivot) posA[++a] = (int32_t)(p + 1);
-        if (k2 >= st.pivot) posA[++a] = (int32_t)(p + 2);
-        if (k3 >= st.pivot) posA[++a] = (int32_t)(p + 3);
+        if (k0 >= st.pivot) posA[++a] = (PosT)(p - f);
+        if (k1 >= st.pivot) posA[++a] = (PosT)(p + 1 - f);
+        if (k2 >= st.pivot) posA[++a] = (PosT)(p + 2 - f);
+        if (k3 >= st.pivot) posA[++a] = (PosT)(p + 3 - f);
     }
     for (; p < e; ++p)
-        if ((uint32_t)(v[p] >> 32) >= st.pivot) posA[++a] = (int32_t)p;
+        if ((uint32_t)(v[p] >> 32) >= st.pivot) posA[++a] = (PosT)(p - f);
     int b = b_right;
     p = e - 1;
     for (; p - 3 >= s; p -= 4) {
         const uint32_t k0 = (uint32_t)(v[p] >> 32), k1 = (uint32_t)(v[p - 1] >> 32);
         const uint32_t k2 = (uint32_t)(v[p - 2] >> 32), k3 = (uint32_t)(v[p - 3] >> 32);
-        if (k0 <= st.pivot) posB[++b] = (int32_t)p;
-        if (k1 <= st.pivot) posB[++b] = (int32_t)(p - 1);
-        if (k2 <= st.pivot) posB[++b] = (int32_t)(p - 2);
-        if (k3 <= st.pivot) posB[++b] = (int32_t)(p - 3);
+        if (k0 <= st.pivot) posB[++b] = (PosT)(p - f);
+        if (k1 <= st.pivot) posB[++b] = (PosT)(p - 1 - f);
+        if (k2 <= st.pivot) posB[++b] = (PosT)(p - 2 - f);
+        if (k3 <= st.pivot) posB[++b] = (PosT)(p - 3 - f);
     }
     for (; p >= s; --p)
-        if ((uint32_t)(v[p] >> 32) <= st.pivot) posB[++b] = (int32_t)p;
+        if ((uint32_t)(v[p] >> 32) <= st.pivot) posB[++b] = (PosT)(p - f);
 }
-B2P_HD int bp_count_swaps(const BlockPartState& st, int tid, int T, const int32_t* posA, const int32_t* posB) {
+template <class PosT>
+B2P_HD int bp_count_swaps(const BlockPartState& st, int tid, int T, const PosT* posA, const PosT* posB) {
     const int lim = st.totA < st.totB ? st.totA : st.totB;
     int c = 0;
     for (int k = 1 + tid; k <= lim; k += T) c += (posA[k] < posB[k]);
     return c;
 }
-B2P_HD void bp_swap(const BlockPartState& st, uint64_t* v, int tid, int T, const int32_t* posA, const int32_t* posB) {
+template <class PosT>
+B2P_HD void bp_swap(const BlockPartState& st, uint64_t* v, int tid, int T, const PosT* posA, const PosT* posB) {
     for (int k = 1 + tid; k <= st.K; k += T) {
-        const uint64_t t = v[posA[k]]; v[posA[k]] = v[posB[k]]; v[posB[k]] = t;
+        const long ia = st.first + posA[k], ib = st.first + posB[k];
+        const uint64_t t = v[ia]; v[ia] = v[ib]; v[ib] = t;
     }
 }
-B2P_HD long bp_cut(const BlockPartState& st, const int32_t* posA, const int32_t* posB) {
-    const long a_next = (st.K + 1 <= st.totA) ? posA[st.K + 1] : st.last;
-    return (st.K > 0 && posB[st.K] < a_next) ? posB[st.K] : a_next;
+template <class PosT>
+B2P_HD long bp_cut(const BlockPartState& st, const PosT* posA, const PosT* posB) {
+    const long a_next = (st.K + 1 <= st.totA) ? st.first + posA[st.K + 1] : st.last;
+    return (st.K > 0 && st.first + posB[st.K] < a_next) ? st.first + posB[st.K] : a_next;
 }
 
 #if !defined(__CUDA_ARCH__)
 // host emulation of one block partition with T virtual threads (tests)
-inline long block_partition_host(uint64_t* v, long first, long last, int T, int32_t* posA, int32_t* posB) {
+template <class PosT>
+inline long block_partition_host(uint64_t* v, long first, long last, int T, PosT* posA, PosT* posB) {
     BlockPartState st;
     bp_prepare(st, v, first, last, T);
     int* cA = new int[T]; int* cB = new int[T];
@@ -472,10 +533,14 @@ B2P_HD void leaf_insertion_sort(uint64_t* v, long first, long last) {
 
 #if !defined(__CUDA_ARCH__)
 // host reference driver of the parallel formulation (tests): same partition routine, explicit stack
-inline void par_std_sort_host(uint64_t* v, int n, int big = 1 << 30, int T = 512) {
+// big: ranges above it use the rank-based partition with T virtual threads and int32 tables; warp_rank: ranges of
+// <= warp_rank keys use the rank-based partition with 32 lanes and uint16 tables of 512 entries (the device warp
+// phase); everything else uses the chunked warp_partition.
+inline void par_std_sort_host(uint64_t* v, int n, int big = 1 << 30, int T = 512, int warp_rank = 0, int seq_small = 0) {
     if (n <= 1) return;
     int32_t* posA = new int32_t[n + 2];
     int32_t* posB = new int32_t[n + 2];
+    uint16_t tabA[512], tabB[512];
     int lg = 0;
     for (int m = n; m > 1; m >>= 1) ++lg;
     long sf[128], sl[128];
@@ -487,15 +552,18 @@ inline void par_std_sort_host(uint64_t* v, int n, int big = 1 << 30, int T = 512
         int depth = sd[sp];
         bool heap_sorted = false;
         while (last - first > 16) {
+            if (last - first <= seq_small) { seq_sort_range(v, first, last, depth); heap_sorted = true; break; }
             if (depth == 0) { seq_heap_sort(v, first, last); heap_sorted = true; break; }
             --depth;
             const long cut = (last - first > big) ? block_partition_host(v, first, last, T, posA, posB)
-                                                  : warp_partition(v, first, last);
+                             : (last - first <= warp_rank) ? block_partition_host(v, first, last, 32, tabA, tabB)
+                                                           : warp_partition(v, first, last);
             if (last - cut > 16) { sf[sp] = cut; sl[sp] = last; sd[sp] = depth; ++sp; }
+            else if (seq_small) seq_sort_range(v, cut, last, depth);
             else leaf_insertion_sort(v, cut, last);
             last = cut;
         }
-        if (!heap_sorted) leaf_insertion_sort(v, first, last);
+        if (!heap_sorted) { if (seq_small) seq_sort_range(v, first, last, depth); else leaf_insertion_sort(v, first, last); }
     }
     delete[] posA; delete[] posB;
 }

@@ -200,6 +200,11 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
 // Together this is exactly __introsort_loop + __final_insertion_sort, including the order of equal keys.
 constexpr int kSortQ = 128, kSortLocal = 40, kLimbWarps = kLimbThreads / 32;
 constexpr int kSmemRange = B2P_SMEM_RANGE, kWarpRange = 512, kBigStack = 80;
+#ifndef B2P_SEQ_RANGE
+#define B2P_SEQ_RANGE 16
+#endif
+constexpr int kSeqRange = B2P_SEQ_RANGE;     // parts of <= kSeqRange keys are batched per warp and sorted one per lane (16 = leaves only
+                                             // measured best: 2249 vs 2135 frames/s with 64; lane divergence eats larger values)
 struct SortShared {
     int lock, top, pending;
     int sf[kSortQ], sl[kSortQ], sd[kSortQ];
@@ -213,6 +218,11 @@ struct SortShared {
     unsigned long long scan2[kLimbThreads / 32 + 1];
     int ksum;
     unsigned char wscr[kLimbWarps][64];     // rank -> lane tables of warp_partition
+    uint16_t* wtab;                         // kLimbWarps x 1024 uint16: per-warp rank -> position tables (warp phase)
+    unsigned long long* dbg;                // optional diagnostics counters
+    // per-warp batch of small ranges (<= kSeqRange keys): sorted one range per lane by seq_sort_range()
+    int bn[kLimbWarps];
+    int bsf[kLimbWarps][32], bsl[kLimbWarps][32], bsd[kLimbWarps][32];
 };
 
 // Stable sort of up to two leaves (<= 16 keys each) by one warp: lanes 0-15 take leaf 0, lanes 16-31 leaf 1; every key's
@@ -259,44 +269,130 @@ __device__ __forceinline__ void block_exclusive_scan2(int a, int b, int* offA, i
     __syncthreads();
 }
 
-// One exact block-level partition of v[f, l) (all threads).  Returns the cut (uniform).
-__device__ int block_partition(uint64_t* v, int f, int l, SortShared& sh, int32_t* posA, int32_t* posB) {
-    const int tid = threadIdx.x;
-    if (tid == 0) { bp_prepare(sh.bp, v, f, l, kLimbThreads); sh.ksum = 0; }
-    __syncthreads();
-    int cA, cB, offA, offBl, totA, totB;
-    bp_count(sh.bp, v, tid, &cA, &cB);
-    block_exclusive_scan2(cA, cB, &offA, &offBl, &totA, &totB, sh.scan2);
-    BlockPartState st = sh.bp;
-    st.totA = totA; st.totB = totB;
-    bp_scatter(st, v, tid, offA, totB - offBl - cB, posA, posB);
-    __syncthreads();
-    int c = bp_count_swaps(st, tid, kLimbThreads, posA, posB);
+// Exact partition of v[f, l) with the rank-based formulation of the Hoare loop (post_core.h: lo-stop #k from the left
+// pairs with hi-stop #k from the right while posA[k] < posB[k]; cut = min(posA[K+1], posB[K])), evaluated ROW-WISE:
+// the range is cut into one contiguous segment per cooperating warp, inside a segment the 32 lanes take consecutive
+// keys (coalesced in global memory, conflict-free in shared memory) and the ranks come from ballots + running counts.
+// kWarps = 1: a single warp (no block barriers); kWarps = kLimbWarps: the whole block.  Tables hold positions relative
+// to f (uint16 for shared-memory ranges, int32 for global ones), 1-based ranks.
+template <class PosT, int kWarps>
+__device__ int rank_partition(uint64_t* v, int f, int l, PosT* tabA, PosT* tabB, SortShared& sh) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wq = (kWarps == 1) ? 0 : (tid >> 5);
+    const uint32_t lt = (1u << lane) - 1u, gt = ~lt & ~(1u << lane);
+    if ((kWarps == 1 ? lane : tid) == 0) {       // __move_median_to_first(first, first+1, mid, last-1)
+        const long a = f + 1, b = f + (l - f) / 2, c = l - 1;
+        long m;
+        if (B2P_COMP(v[a], v[b])) m = B2P_COMP(v[b], v[c]) ? b : (B2P_COMP(v[a], v[c]) ? c : a);
+        else m = B2P_COMP(v[a], v[c]) ? a : (B2P_COMP(v[b], v[c]) ? c : b);
+        const uint64_t t = v[f]; v[f] = v[m]; v[m] = t;
+        if (kWarps > 1) sh.ksum = 0;
+    }
+    if (kWarps == 1) __syncwarp(); else __syncthreads();
+    const uint32_t pivot = (uint32_t)(v[f] >> 32);
+    const int base = f + 1;
+    const int rows = (l - base + 31) >> 5;
+    const int rpw = (rows + kWarps - 1) / kWarps;             // rows per warp
+    const int r0 = min(rows, wq * rpw), r1 = min(rows, r0 + rpw);
+    // pass 1: stop counts of this warp's segment
+    int cA = 0, cB = 0;
+    for (int r = r0; r < r1; ++r) {
+        const int p = base + (r << 5) + lane;
+        const uint32_t k = p < l ? (uint32_t)(v[p] >> 32) : 0u;
+        cA += __popc(__ballot_sync(0xffffffffu, p < l && k >= pivot));
+        cB += __popc(__ballot_sync(0xffffffffu, p < l && k <= pivot));
+    }
+    int offA = 0, offB = 0, totA = cA, totB = cB;
+    if (kWarps > 1) {
+        if (lane == 0) sh.scan2[wq] = ((unsigned long long)(unsigned)cB << 32) | (unsigned)cA;
+        __syncthreads();
+        unsigned long long pre = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < kWarps; ++k) {
+            const unsigned long long c = sh.scan2[k];
+            if (k < wq) pre += c;
+            tot += c;
+        }
+        offA = (int)(unsigned)pre; offB = (int)(pre >> 32);
+        totA = (int)(unsigned)tot; totB = (int)(tot >> 32);
+    }
+    // pass 2: lo-stops, ranked from the left
+    int run = offA;
+    for (int r = r0; r < r1; ++r) {
+        const int p = base + (r << 5) + lane;
+        const bool st = p < l && (uint32_t)(v[p] >> 32) >= pivot;
+        const uint32_t m = __ballot_sync(0xffffffffu, st);
+        if (st) tabA[run + __popc(m & lt) + 1] = (PosT)(p - f);
+        run += __popc(m);
+    }
+    // pass 3: hi-stops, ranked from the right
+    run = totB - offB - cB;                                   // hi-stops in the segments to the right
+    for (int r = r1 - 1; r >= r0; --r) {
+        const int p = base + (r << 5) + lane;
+        const bool st = p < l && (uint32_t)(v[p] >> 32) <= pivot;
+        const uint32_t m = __ballot_sync(0xffffffffu, st);
+        if (st) tabB[run + __popc(m & gt) + 1] = (PosT)(p - f);
+        run += __popc(m);
+    }
+    if (kWarps == 1) __syncwarp(); else __syncthreads();
+    // K = number of leading ranks with posA[k] < posB[k] (monotone)
+    const int lim = totA < totB ? totA : totB;
+    const int nthr = kWarps * 32, me = (kWarps == 1) ? lane : tid;
+    int c = 0;
+    for (int k = 1 + me; k <= lim; k += nthr) c += (tabA[k] < tabB[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((tid & 31) == 0 && c) atomicAdd(&sh.ksum, c);
-    __syncthreads();
-    st.K = sh.ksum;
-    bp_swap(st, v, tid, kLimbThreads, posA, posB);
-    __syncthreads();
-    return (int)bp_cut(st, posA, posB);
+    int K = c;
+    if (kWarps > 1) {
+        if (lane == 0 && c) atomicAdd(&sh.ksum, c);
+        __syncthreads();
+        K = sh.ksum;
+    }
+    for (int k = 1 + me; k <= K; k += nthr) {
+        const int ia = f + tabA[k], ib = f + tabB[k];
+        const uint64_t t = v[ia]; v[ia] = v[ib]; v[ib] = t;
+    }
+    const int a_next = (K + 1 <= totA) ? f + (int)tabA[K + 1] : l;
+    const int cut = (K > 0 && f + (int)tabB[K] < a_next) ? f + (int)tabB[K] : a_next;
+    if (kWarps == 1) __syncwarp(); else __syncthreads();
+    return cut;
+}
+
+// Small ranges (<= kSeqRange keys) are not worth a warp-cooperative partition (a 32-key partition costs as many
+// instructions as a 256-key one): the warp collects them and sorts 32 of them at once, one range per lane, with the
+// sequential exact routine.
+__device__ __forceinline__ void small_flush(SortShared& sh, uint64_t* v) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = __shfl_sync(0xffffffffu, sh.bn[warp], 0);
+    if (lane < n) seq_sort_range(v, sh.bsf[warp][lane], sh.bsl[warp][lane], sh.bsd[warp][lane]);
+    __syncwarp();
+    if (lane == 0) sh.bn[warp] = 0;
+    __syncwarp();
+}
+__device__ __forceinline__ void small_add(SortShared& sh, uint64_t* v, int f, int l, int d) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = sh.bn[warp];
+    __syncwarp();       // every lane holds the OLD count before lane 0 bumps it (lanes are not in lock step: a late reader
+                        // would otherwise disagree on "batch full" and diverge around the barriers of small_flush)
+    if (lane == 0) { sh.bsf[warp][n] = f; sh.bsl[warp][n] = l; sh.bsd[warp][n] = d; sh.bn[warp] = n + 1; }
+    __syncwarp();
+    if (n + 1 == 32) small_flush(sh, v);
 }
 
 // Left-descending introsort loop of one warp on v[f, l): partitions, hands the right parts to the shared stack (or its
-// own local stack), leaf-sorts parts of <= 16 keys.
+// own local stack), batches parts of <= kSeqRange keys for the per-lane sequential sort.
 __device__ void warp_descend(uint64_t* v, int f, int l, int d, SortShared& sh) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool heap_sorted = false;
-    while (l - f > 16) {
+    while (l - f > kSeqRange) {
         if (d == 0) {                      // depth limit exhausted: std::__partial_sort == heap sort
             if (lane == 0) seq_heap_sort(v, f, l);
             __syncwarp();
-            heap_sorted = true;
-            break;
+            return;
         }
         --d;
-        const int cut = (int)warp_partition(v, f, l, sh.wscr[warp]);
-        if (l - cut > 16) {
+        const int cut = (l - f <= 512) ? rank_partition<uint16_t, 1>(v, f, l, sh.wtab + warp * 1024, sh.wtab + warp * 1024 + 512, sh)
+                                       : (int)warp_partition(v, f, l, sh.wscr[warp]);
+        if (l - cut > kSeqRange) {
             if (lane == 0) {
                 __threadfence_block();
                 atomicAdd(&sh.pending, 1);
@@ -308,16 +404,16 @@ __device__ void warp_descend(uint64_t* v, int f, int l, int d, SortShared& sh) {
                 if (!pushed) {
                     const int t = sh.ltop[warp];
                     if (t < kSortLocal) { sh.lf[warp][t] = cut; sh.ll[warp][t] = l; sh.ld[warp][t] = d; sh.ltop[warp] = t + 1; }
-                    else { seq_std_sort(v + cut, l - cut); atomicSub(&sh.pending, 1); }   // unreachable (depth bound)
+                    else { seq_sort_range(v, cut, l, d); atomicSub(&sh.pending, 1); }   // unreachable (depth bound)
                 }
             }
-        } else {
-            warp_sort_two_leaves(v, cut, l, 0, 0);
+        } else if (l - cut > 1) {
+            small_add(sh, v, cut, l, d);
         }
         l = cut;
         __syncwarp();
     }
-    if (!heap_sorted) warp_sort_two_leaves(v, f, l, 0, 0);
+    if (l - f > 1) small_add(sh, v, f, l, d);
     __syncwarp();
 }
 
@@ -328,8 +424,12 @@ __device__ void smem_sort_range(uint64_t* w, int f, int l, int d, SortShared& sh
                                 unsigned long long* dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long t0 = clock64();
-    if (tid == 0) { sh.lock = 0; sh.top = 0; sh.pending = 0; sh.s_top = 1; sh.s_f[0] = f; sh.s_l[0] = l; sh.s_d[0] = d; }
-    if (tid < kLimbWarps) sh.ltop[tid] = 0;
+    if (tid == 0) {
+        sh.dbg = dbg;
+        sh.lock = 0; sh.top = 0; sh.pending = 0; sh.s_top = 1; sh.s_f[0] = f; sh.s_l[0] = l; sh.s_d[0] = d;
+        sh.wtab = reinterpret_cast<uint16_t*>(scrA);     // the block-phase scratch is idle during the warp phase
+    }
+    if (tid < kLimbWarps) { sh.ltop[tid] = 0; sh.bn[tid] = 0; }
     __syncthreads();
     // block phase: ranges > kWarpRange
     for (;;) {
@@ -352,7 +452,7 @@ __device__ void smem_sort_range(uint64_t* w, int f, int l, int d, SortShared& sh
         if (kind == 0) break;
         if (kind == 2) { __syncthreads(); continue; }
         const int cf = sh.cur_f, cl = sh.cur_l, cd = sh.cur_d;
-        const int cut = block_partition(w, cf, cl, sh, scrA, scrB);
+        const int cut = rank_partition<int32_t, kLimbWarps>(w, cf, cl, scrA, scrB, sh);
         if (tid == 0) {
             int t = sh.s_top;
             sh.s_f[t] = cf; sh.s_l[t] = cut; sh.s_d[t] = cd; ++t;
@@ -383,8 +483,13 @@ __device__ void smem_sort_range(uint64_t* w, int f, int l, int d, SortShared& sh
             }
         }
         state = __shfl_sync(0xffffffffu, state, 0);
+        {
+            const int have = __shfl_sync(0xffffffffu, sh.bn[warp], 0);   // one lane's view, broadcast
+            if (state != 1 && have > 0) small_flush(sh, w);            // nothing else to do: sort the batched small ranges
+        }
         if (state == 2) break;
         if (state == 0) {
+            if (sh.dbg && lane == 0) atomicAdd(sh.dbg + 14, 1ull);
             if (++idle > (1u << 24)) { printf("[b200pose] exact sort: idle watchdog (block %d,%d)\n", (int)blockIdx.x, (int)blockIdx.y); __trap(); }
             __nanosleep(1000);
             continue;
@@ -394,7 +499,9 @@ __device__ void smem_sort_range(uint64_t* w, int f, int l, int d, SortShared& sh
         rl = __shfl_sync(0xffffffffu, rl, 0);
         rd = __shfl_sync(0xffffffffu, rd, 0);
         __threadfence_block();                 // see the swaps of the warp that published this range
+        const long long td0 = clock64();
         warp_descend(w, rf, rl, rd, sh);
+        if (sh.dbg && lane == 0) atomicAdd(sh.dbg + 12, (unsigned long long)(clock64() - td0));
         if (lane == 0) { __threadfence_block(); atomicSub(&sh.pending, 1); }
     }
     __syncthreads();
@@ -413,7 +520,7 @@ __device__ void block_exact_sort(uint64_t* keys, int n, SortShared& sh, uint64_t
     int32_t* sA = smem_scr;
     int32_t* sB = smem_scr + kSmemRange + 2;
     if (keys == smem_keys) {
-        smem_sort_range(keys, 0, n, 2 * lg, sh, sA, sB, nullptr);
+        smem_sort_range(keys, 0, n, 2 * lg, sh, sA, sB, dbg);
         return;
     }
     if (tid == 0) { sh.g_top = 1; sh.g_f[0] = 0; sh.g_l[0] = n; sh.g_d[0] = 2 * lg; }
@@ -437,7 +544,7 @@ __device__ void block_exact_sort(uint64_t* keys, int n, SortShared& sh, uint64_t
             __syncthreads();
         } else {
             const long long tg = clock64();
-            const int cut = block_partition(keys, f, l, sh, gA, gB);
+            const int cut = rank_partition<int32_t, kLimbWarps>(keys, f, l, gA, gB, sh);
             if (dbg && tid == 0) { atomicAdd(dbg + 5, (unsigned long long)(clock64() - tg)); atomicAdd(dbg + 8, 1ull); }
             if (tid == 0) {
                 int q = sh.g_top;
@@ -450,20 +557,21 @@ __device__ void block_exact_sort(uint64_t* keys, int n, SortShared& sh, uint64_t
     __syncthreads();
 }
 
-// Greedy one-to-one assignment (pafprocess.cpp:98-124) by one warp, 32 sorted candidates per step; conflicts inside
-// a chunk are resolved in candidate order, so the result equals the sequential loop.
-__device__ int greedy_match_warp(const uint64_t* keys, int n, int nb, uint32_t* used_a, uint32_t* used_b, int max_conn,
-                                 int* conn_a, int* conn_b, float* conn_s) {
+// Greedy one-to-one assignment (pafprocess.cpp:98-124).  The sorted list is walked in segments of kSmemRange
+// candidates: all threads first drop the candidates whose end points were already taken by earlier segments (ordered
+// compaction into shared memory), then one warp runs the sequential rule over the survivors only, 32 per step, resolving
+// conflicts inside a chunk in candidate order.  Identical to the sequential loop: a candidate rejected by the pre-filter
+// would be rejected sequentially too, survivors are examined in order against the live used-sets.
+__device__ int greedy_warp_chunked(const uint64_t* keys, int n, int nb, uint32_t* used_a, uint32_t* used_b, int max_conn,
+                                   int nc, int* conn_a, int* conn_b, float* conn_s) {
     const int lane = threadIdx.x & 31;
-    int nc = 0;
-    uint64_t k_next = lane < n ? keys[lane] : 0;           // software pipelining: chunk i+1 is in flight while i is matched
     for (int base = 0; base < n && nc < max_conn; base += 32) {
         const int i = base + lane;
-        const uint64_t k = k_next;
-        if (i + 32 < n) k_next = keys[i + 32];
+        uint64_t k = 0;
         int a = -1, b = -1;
         bool free_ = false;
         if (i < n) {
+            k = keys[i];
             const uint32_t pair = (uint32_t)k;
             a = pair / nb;
             b = pair - a * nb;
@@ -486,6 +594,45 @@ __device__ int greedy_match_warp(const uint64_t* keys, int n, int nb, uint32_t* 
         __syncwarp();
     }
     return nc;
+}
+
+constexpr int kGreedyPer = kSmemRange / kLimbThreads;    // candidates per thread and segment
+
+__device__ int greedy_segmented(const uint64_t* keys, int n, int nb, uint32_t* used_a, uint32_t* used_b, int max_conn,
+                                int* conn_a, int* conn_b, float* conn_s, uint64_t* seg /*smem, kSmemRange*/,
+                                int* scan_scratch, int* s_nc) {
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_nc = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < n; s0 += kSmemRange) {
+        if (*s_nc >= max_conn) break;
+        uint64_t kk[kGreedyPer];
+        int keep = 0, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kGreedyPer; ++j) {
+            const int i = s0 + tid * kGreedyPer + j;
+            kk[j] = 0;
+            if (i < n) {
+                kk[j] = keys[i];
+                const uint32_t pair = (uint32_t)kk[j];
+                const int a = pair / nb, b = pair - a * nb;
+                if (!((used_a[a >> 5] >> (a & 31)) & 1u) && !((used_b[b >> 5] >> (b & 31)) & 1u)) { keep |= 1 << j; ++cnt; }
+            }
+        }
+        int m;
+        int off = block_exclusive_scan(cnt, &m, scan_scratch);     // (barriers inside: every key of the segment is in registers now)
+#pragma unroll
+        for (int j = 0; j < kGreedyPer; ++j)
+            if ((keep >> j) & 1) seg[off++] = kk[j];
+        __syncthreads();
+        if (tid < 32) {
+            const int nc = greedy_warp_chunked(seg, m, nb, used_a, used_b, max_conn, *s_nc, conn_a, conn_b, conn_s);
+            __syncwarp();
+            if (tid == 0) *s_nc = nc;
+        }
+        __syncthreads();
+    }
+    return *s_nc;
 }
 
 __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up, int lw,
@@ -613,10 +760,12 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     block_exact_sort(reinterpret_cast<uint64_t*>(keys), n, s_sort, reinterpret_cast<uint64_t*>(sm_keys), sm_scr, posA,
                      posB, pb.dbg);     // std::sort, pafprocess.cpp:97
     const long long t_sorted = clock64();
-    if (tid < 32) {
+    {
+        __shared__ int s_nc;
         const long o = ((long)img * kNumLimb + limb) * cap;
-        const int nc = greedy_match_warp(reinterpret_cast<const uint64_t*>(keys), n, nb, used_a, used_b, min(na, nb),
-                                         pb.conn_a + o, pb.conn_b + o, pb.conn_s + o);
+        const int nc = greedy_segmented(reinterpret_cast<const uint64_t*>(keys), n, nb, used_a, used_b, min(na, nb),
+                                        pb.conn_a + o, pb.conn_b + o, pb.conn_s + o, reinterpret_cast<uint64_t*>(sm_keys),
+                                        scan_scratch, &s_nc);
         if (tid == 0) {
             *out_cnt = nc;
             if (pb.dbg) {   // phase maxima over blocks (cycles): scoring+compaction, sort, greedy; and max candidates

@@ -114,6 +114,8 @@ extern "C" int core_sort_check(uint64_t* keys, int n, uint64_t* out) {
     par_std_sort_host(par.data(), n);                 // warp-chunked partition everywhere
     par_std_sort_host(blk.data(), n, 64, 7);          // rank-based block partition for ranges > 64, 7 virtual threads
     par_std_sort_host(blk2.data(), n, 300, 512);      // ... > 300 with 512 virtual threads (mostly empty slices)
+    std::vector<uint64_t> dev(keys, keys + n);        // the device configuration: > 512 block-level, <= 512 warp rank tables
+    par_std_sort_host(dev.data(), n, 512, 512, 512, 64);   // + ranges <= 64 by the per-lane sequential sort
     for (int i = 0; i < n; ++i) out[i] = par[i];
-    return (seq == par ? 0 : 1) | (seq == blk ? 0 : 2) | (seq == blk2 ? 0 : 4);
+    return (seq == par ? 0 : 1) | (seq == blk ? 0 : 2) | (seq == blk2 ? 0 : 4) | (seq == dev ? 0 : 8);
 }
