@@ -110,6 +110,28 @@ int b200pose_infer_u8(b200pose_net* net, b200pose_post* post, const unsigned cha
                       int H, int W, int mode, float thresh, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * 3b. Flip test-time averaging: replaces handle_paf_and_heat        evaluate/coco_eval.py:197-242
+ *     out = (normal + mirror_W(flipped)[left/right-swapped channels, PAF x components negated]) / 2, bit-identical to
+ *     the reference's float32 arithmetic.  Unlike the reference it does not modify flipped_paf in place.
+ *     All six pointers are host (on_device = 0; copies on `cuda_stream`, synchronised before return) or device (1,
+ *     asynchronous); layout 0 = [n,C,h,w], 1 = [n,h,w,C] (what get_outputs returns per image), C = 19 / 38.
+ *     `post` provides the device and the staging buffers.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200pose_flip_merge(b200pose_post* post, const float* normal_heat, const float* flipped_heat,
+                        const float* normal_paf, const float* flipped_paf, int on_device, int layout, int n, int h, int w,
+                        float* out_heat, float* out_paf, void* cuda_stream);
+/* Fused flip-TTA inference: the n frames and their W-mirrored copies (made on the device) run through the network as
+ * one 2n batch, the two map sets are merged as above and the fused post-processing runs on the averaged maps; nothing
+ * leaves the device but the person rows.  Equivalent to get_outputs(img) + get_outputs(img[:, ::-1]) +
+ * handle_paf_and_heat + paf_to_pose_cpp for frames that need no padding in W (a padded frame must be mirrored before
+ * crop_with_factor pads it: use b200pose_net_forward on both orientations + b200pose_flip_merge instead).
+ * Results are fetched exactly like b200pose_infer's. */
+int b200pose_infer_flip(b200pose_net* net, b200pose_post* post, const float* input, int input_on_device, int n, int H,
+                        int W, int mode, float thresh, void* cuda_stream);
+int b200pose_infer_u8_flip(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device,
+                           int n, int H, int W, int mode, float thresh, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * 4. Legacy SWIG surface of lib/pafprocess (pafprocess.h:53-59, pafprocess.i:14): same names, same argument
  *    meaning; state is kept in a process-global context exactly like the reference's file-scope globals
  *    (pafprocess.cpp:12-13).  peaks [p1,p2,5] rows (x, y, score, id, part) sorted by part as paf_to_pose_cpp

@@ -53,6 +53,9 @@ def lib():
         "b200pose_post_get_peaks": ([vp, ci, vp, ci], ci),
         "b200pose_infer": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
         "b200pose_infer_u8": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
+        "b200pose_flip_merge": ([vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp], ci),
+        "b200pose_infer_flip": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
+        "b200pose_infer_u8_flip": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
         "process_paf": ([ci, ci, ci, vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
         "get_num_humans": ([], ci),
         "get_part_cid": ([ci, ci], ci),
@@ -73,7 +76,8 @@ EXPORTED = ["b200pose_last_error", "b200pose_version", "b200pose_launch_count", 
             "b200pose_net_destroy", "b200pose_net_tensor_shape", "b200pose_net_set_tensor", "b200pose_net_finalize",
             "b200pose_net_forward", "b200pose_net_forward_u8", "b200pose_net_profile", "b200pose_net_last_maps", "b200pose_post_create", "b200pose_post_destroy",
             "b200pose_post_run", "b200pose_post_sync", "b200pose_post_last_ticket", "b200pose_post_select", "b200pose_post_debug", "b200pose_post_num_humans", "b200pose_post_status",
-            "b200pose_post_get_humans", "b200pose_post_get_peaks", "b200pose_infer", "b200pose_infer_u8", "process_paf", "get_num_humans",
+            "b200pose_post_get_humans", "b200pose_post_get_peaks", "b200pose_infer", "b200pose_infer_u8", "b200pose_flip_merge", "b200pose_infer_flip",
+            "b200pose_infer_u8_flip", "process_paf", "get_num_humans",
             "get_part_cid", "get_score", "get_part_x", "get_part_y", "get_part_score"]
 
 

@@ -14,6 +14,7 @@
 #include "conv_misc.cuh"
 #include "conv_tc.cuh"
 #include "postprocess.cuh"
+#include "tta.cuh"
 
 using namespace b2p;
 
@@ -153,6 +154,7 @@ struct b200pose_post {
     int device = 0;
     PostBuffers pb{};
     DevBuf<float> d_heat, d_paf;
+    DevBuf<float> tta_in, tta_out;   // b200pose_flip_merge staging for host pointers
     // Results are copied to pinned host memory by the run itself (second stream, right after the assembly) into one
     // of two slots selected by the run's parity, so the host can fetch run i while run i+1 is in flight.
     cudaStream_t s2 = nullptr;
@@ -609,6 +611,7 @@ void b200pose_post_destroy(b200pose_post* p) {
     if (p->s2) cudaStreamSynchronize(p->s2);
     post_free(p->pb);
     p->d_heat.release(); p->d_paf.release();
+    p->tta_in.release(); p->tta_out.release();
     for (int b = 0; b < 2; ++b) {
         if (p->ev_fetch[b]) cudaEventDestroy(p->ev_fetch[b]);
         if (p->hp_nh[b]) cudaFreeHost(p->hp_nh[b]);
@@ -770,6 +773,96 @@ int b200pose_infer(b200pose_net* net, b200pose_post* post, const float* input, i
 int b200pose_infer_u8(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device, int n,
                       int H, int W, int mode, float thresh, void* cuda_stream) {
     return infer_impl(net, post, images, 1, input_on_device, n, H, W, mode, thresh, cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------------ flip TTA
+static int flip_merge_dev(const float* nh, const float* fh, const float* np_, const float* fp, int layout, int n, int h,
+                          int w, float* oh, float* op, cudaStream_t st) {
+    cudaError_t e;
+    if (layout == 0) {
+        e = tta_flip_merge(nh, fh, oh, n, kHeat, h, w, (long)h * w, w, 1, st);
+        if (e == cudaSuccess) e = tta_flip_merge(np_, fp, op, n, kPaf, h, w, (long)h * w, w, 1, st);
+    } else {
+        e = tta_flip_merge(nh, fh, oh, n, kHeat, h, w, 1, (long)w * kHeat, kHeat, st);
+        if (e == cudaSuccess) e = tta_flip_merge(np_, fp, op, n, kPaf, h, w, 1, (long)w * kPaf, kPaf, st);
+    }
+    if (e != cudaSuccess) return fail("tta_flip_merge: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    return 0;
+}
+
+int b200pose_flip_merge(b200pose_post* p, const float* normal_heat, const float* flipped_heat, const float* normal_paf,
+                        const float* flipped_paf, int on_device, int layout, int n, int h, int w, float* out_heat,
+                        float* out_paf, void* cuda_stream) {
+    if (!p) return fail("null post");
+    if (n < 1 || h < 1 || w < 1 || (layout != 0 && layout != 1)) return fail("flip_merge: bad shape / layout");
+    if (!normal_heat || !flipped_heat || !normal_paf || !flipped_paf || !out_heat || !out_paf) return fail("flip_merge: null pointer");
+    CU(cudaSetDevice(p->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (on_device)
+        return flip_merge_dev(normal_heat, flipped_heat, normal_paf, flipped_paf, layout, n, h, w, out_heat, out_paf, st);
+    const size_t eh = (size_t)n * kHeat * h * w, ep = (size_t)n * kPaf * h * w;
+    CU(p->tta_in.ensure(2 * (eh + ep)));
+    CU(p->tta_out.ensure(eh + ep));
+    float *d_nh = p->tta_in.p, *d_fh = d_nh + eh, *d_np = d_fh + eh, *d_fp = d_np + ep;
+    float *d_oh = p->tta_out.p, *d_op = d_oh + eh;
+    CU(cudaMemcpyAsync(d_nh, normal_heat, eh * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_fh, flipped_heat, eh * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_np, normal_paf, ep * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_fp, flipped_paf, ep * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = flip_merge_dev(d_nh, d_fh, d_np, d_fp, layout, n, h, w, d_oh, d_op, st)) return rc;
+    CU(cudaMemcpyAsync(out_heat, d_oh, eh * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_paf, d_op, ep * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int infer_flip_impl(b200pose_net* net, b200pose_post* post, const void* input, int in_u8, int input_on_device,
+                           int n, int H, int W, int mode, float thresh, void* cuda_stream) {
+    if (!net || !post) return fail("null handle");
+    if (!net->finalized) return fail("net not finalized");
+    if (net->device != post->device) return fail("net and post live on different devices");
+    if (n < 1 || H < 8 || W < 8 || (H % 8) || (W % 8)) return fail("input must be [n,3,H,W] with H, W multiples of 8");
+    if (n > post->pb.batch_cap) return fail("batch %d exceeds post batch_cap %d", n, post->pb.batch_cap);
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    // the 2n batch [frames | mirrored frames] is assembled in the net's staging buffer
+    const size_t elems = (size_t)n * 3 * H * W;
+    const cudaMemcpyKind kind = input_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const void* d_batch;
+    cudaError_t e;
+    if (in_u8) {
+        CU(net->in_stage_u8.ensure(2 * elems));
+        CU(cudaMemcpyAsync(net->in_stage_u8.p, input, elems, kind, st));
+        e = tta_mirror_u8hwc(net->in_stage_u8.p, net->in_stage_u8.p + elems, n, H, W, st);
+        d_batch = net->in_stage_u8.p;
+    } else {
+        CU(net->in_stage.ensure(2 * elems));
+        CU(cudaMemcpyAsync(net->in_stage.p, input, elems * 4, kind, st));
+        e = tta_mirror_f32(net->in_stage.p, net->in_stage.p + elems, (long)n * 3, H, W, st);
+        d_batch = net->in_stage.p;
+    }
+    if (e != cudaSuccess) return fail("tta_mirror: %s", cudaGetErrorString(e));
+    ++g_launches;
+    int rc = net_forward_impl(net, d_batch, in_u8, 1, 2 * n, H, W, mode, nullptr, 1, st, false);
+    if (rc) return rc;
+    const int h = H / 8, w = W / 8;
+    const size_t eh = (size_t)n * kHeat * h * w, ep = (size_t)n * kPaf * h * w;
+    CU(post->d_heat.ensure(eh));
+    CU(post->d_paf.ensure(ep));
+    rc = flip_merge_dev(net->out_f32[11].p, net->out_f32[11].p + eh, net->out_f32[10].p, net->out_f32[10].p + ep, 0, n, h,
+                        w, post->d_heat.p, post->d_paf.p, st);
+    if (rc) return rc;
+    return post_run_dev(post, post->d_heat.p, post->d_paf.p, 0, n, h, w, thresh, st);
+}
+
+int b200pose_infer_flip(b200pose_net* net, b200pose_post* post, const float* input, int input_on_device, int n, int H,
+                        int W, int mode, float thresh, void* cuda_stream) {
+    return infer_flip_impl(net, post, input, 0, input_on_device, n, H, W, mode, thresh, cuda_stream);
+}
+int b200pose_infer_u8_flip(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device,
+                           int n, int H, int W, int mode, float thresh, void* cuda_stream) {
+    return infer_flip_impl(net, post, images, 1, input_on_device, n, H, W, mode, thresh, cuda_stream);
 }
 
 // ------------------------------------------------------------------------------------------------ legacy pafprocess

@@ -63,6 +63,28 @@ class NativePost:
                                               layout, n, h, w, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
                   "b200pose_post_run")
 
+    def flip_merge(self, normal_heat, flipped_heat, normal_paf, flipped_paf, layout=1):
+        """Device-side handle_paf_and_heat (evaluate/coco_eval.py:197-242) on host float32 arrays.
+        layout 1: heat [n,h,w,19] / paf [n,h,w,38] (or a single image [h,w,C]); layout 0: [n,C,h,w].
+        Returns (averaged_paf, averaged_heat) like the reference; the inputs are not modified."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (normal_heat, flipped_heat, normal_paf, flipped_paf)]
+        single = arrs[0].ndim == 3
+        if single:
+            arrs = [a[None] for a in arrs]
+        if layout == 1:
+            n, h, w, ch = arrs[0].shape
+            cp = arrs[2].shape[3]
+        else:
+            n, ch, h, w = arrs[0].shape
+            cp = arrs[2].shape[1]
+        if ch != 19 or cp != 38 or arrs[1].shape != arrs[0].shape or arrs[3].shape != arrs[2].shape:
+            raise nat.B200PoseError("flip_merge: expected heat with 19 and paf with 38 channels, equal shapes")
+        out_heat, out_paf = np.empty_like(arrs[0]), np.empty_like(arrs[2])
+        nat.check(nat.lib().b200pose_flip_merge(self._h, *[ctypes.c_void_p(a.ctypes.data) for a in arrs], 0, int(layout),
+                                                n, h, w, ctypes.c_void_p(out_heat.ctypes.data),
+                                                ctypes.c_void_p(out_paf.ctypes.data), None), "b200pose_flip_merge")
+        return (out_paf[0], out_heat[0]) if single else (out_paf, out_heat)
+
     def sync(self):
         nat.check(nat.lib().b200pose_post_sync(self._h), "b200pose_post_sync")
 
@@ -150,6 +172,22 @@ class PoseEngine:
         self._last = (n, H, W)
         return self.post.last_ticket()
 
+    def infer_flip_async(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
+        """Flip test-time averaging (fp32 NCHW input): frames + device-made mirrored copies as one 2n batch, maps merged
+        as handle_paf_and_heat does, post-processing on the averaged maps."""
+        nat.check(nat.lib().b200pose_infer_flip(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n,
+                                                H, W, self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
+                  "b200pose_infer_flip")
+        self._last = (n, H, W)
+        return self.post.last_ticket()
+
+    def infer_flip_async_u8(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
+        nat.check(nat.lib().b200pose_infer_u8_flip(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device),
+                                                   n, H, W, self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
+                  "b200pose_infer_u8_flip")
+        self._last = (n, H, W)
+        return self.post.last_ticket()
+
     def fetch(self, check=True, ticket=None):
         """Results of run `ticket` (default: the latest).  Up to two runs may be in flight: submit i+1, then fetch i."""
         n, H, W = self._last
@@ -161,19 +199,22 @@ class PoseEngine:
             self.post.check_status(n)
         return [humans_to_dicts(self.post.humans(i), W, H) for i in range(n)]
 
-    def infer_batch(self, images, thresh=0.1):
+    def infer_batch(self, images, thresh=0.1, flip=False):
         """images: uint8 numpy [n,H,W,3] (BGR frames, preprocessing fused on the device), float32 numpy [n,3,H,W]
-        (already preprocessed, host) or a CUDA float tensor.  Returns per-image human lists."""
+        (already preprocessed, host) or a CUDA float tensor.  Returns per-image human lists.
+        flip=True: left/right flip test-time averaging on the device (handle_paf_and_heat semantics)."""
+        run_u8 = self.infer_flip_async_u8 if flip else self.infer_async_u8
+        run_f32 = self.infer_flip_async if flip else self.infer_async
         if isinstance(images, np.ndarray) and images.dtype == np.uint8:
             images = np.ascontiguousarray(images)
             n, H, W, _ = images.shape          # [n,H,W,3] BGR, already cropped/padded to multiples of 8
             self._keep = images
-            self.infer_async_u8(images.ctypes.data, False, n, H, W, thresh)
+            run_u8(images.ctypes.data, False, n, H, W, thresh)
         elif isinstance(images, np.ndarray):
             images = np.ascontiguousarray(images, dtype=np.float32)
             n, _, H, W = images.shape
             self._keep = images
-            self.infer_async(images.ctypes.data, False, n, H, W, thresh)
+            run_f32(images.ctypes.data, False, n, H, W, thresh)
         else:
             import torch
             if not images.is_cuda:
@@ -181,5 +222,5 @@ class PoseEngine:
             images = images.contiguous().float()
             n, _, H, W = images.shape
             self._keep = images
-            self.infer_async(images.data_ptr(), True, n, H, W, thresh, torch.cuda.current_stream().cuda_stream)
+            run_f32(images.data_ptr(), True, n, H, W, thresh, torch.cuda.current_stream().cuda_stream)
         return self.fetch()

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/post_core.h"
+#include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/tta_core.h"
 
 using namespace b2p;
 
@@ -118,4 +119,25 @@ extern "C" int core_sort_check(uint64_t* keys, int n, uint64_t* out) {
     par_std_sort_host(dev.data(), n, 512, 512, 512, 64);   // + ranges <= 64 by the per-lane sequential sort
     for (int i = 0; i < n; ++i) out[i] = par[i];
     return (seq == par ? 0 : 1) | (seq == blk ? 0 : 2) | (seq == blk2 ? 0 : 4) | (seq == dev ? 0 : 8);
+}
+
+// flip test-time averaging with the exact functions the CUDA kernel calls (csrc/tta_core.h); layout 0 = [n,C,h,w],
+// 1 = [n,h,w,C].  Returns the number of channel-table mismatches between the arithmetic permutation and the tables.
+extern "C" int core_flip_merge(const float* normal, const float* flipped, float* out, int n, int channels, int h, int w,
+                               int layout) {
+    static const int SH[19] = B2P_SWAP_HEAT;
+    static const int SP[38] = B2P_SWAP_PAF;
+    int bad = 0;
+    for (int c = 0; c < 19; ++c) bad += tta_swap_channel(false, c) != SH[c];
+    for (int c = 0; c < 38; ++c) bad += tta_swap_channel(true, c) != SP[c];
+    const bool paf = channels == kTtaPaf;
+    const long per = (long)channels * h * w;
+    const long sc = layout == 0 ? (long)h * w : 1, sy = layout == 0 ? w : (long)w * channels, sx = layout == 0 ? 1 : channels;
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < channels; ++c)
+            for (int y = 0; y < h; ++y)
+                for (int x = 0; x < w; ++x)
+                    out[i * per + c * sc + y * sy + x * sx] =
+                        tta_flip_merge_at(normal + i * per, flipped + i * per, paf, c, y, x, w, sc, sy, sx);
+    return bad;
 }

@@ -1,0 +1,76 @@
+"""GPU (-m gpu): flip test-time averaging on the device against the oracle's
+handle_paf_and_heat, the reference's golden vector and the reference-shaped composition
+get_outputs(img) + get_outputs(img[:, ::-1]) + handle_paf_and_heat + paf_to_pose."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, assert_humans_equal, golden, pkg_module
+from oracle import glue_port, pafprocess_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_flip_harness_through_the_c_abi(built):
+    """tests/cuda/test_flip.cpp: fused b200pose_infer*_flip == forward x2 + host merge + post_run, bit for bit, in all
+    three arithmetic modes; merge kernel == host core in both layouts."""
+    r = subprocess.run([os.path.join(ROOT, "build", "test_flip"), "184", "248"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0 and "FLIP TEST OK" in r.stdout, r.stdout[-2000:]
+
+
+def test_flip_merge_kernel_matches_reference_golden(built):
+    eng = pkg_module("engine")
+    post = eng.NativePost(0, batch_cap=1, peak_cap=64, human_cap=64)
+    nh, fh, npf, fpf = [np.random.RandomState(sd).rand(6, 5, c).astype(np.float32)
+                        for sd, c in ((1, 19), (2, 19), (3, 38), (4, 38))]
+    keep = fpf.copy()
+    ap, ah = post.flip_merge(nh, fh, npf, fpf)
+    f = golden("flip_merge")                   # produced by the reference's handle_paf_and_heat
+    np.testing.assert_array_equal(ap, f["avg_paf"])
+    np.testing.assert_array_equal(ah, f["avg_heat"])
+    np.testing.assert_array_equal(fpf, keep)   # documented deviation: inputs are not modified in place
+    # batch, both layouts, signed values
+    rs = np.random.RandomState(9)
+    bnh, bfh, bnp, bfp = (rs.randn(3, 46, 53, c).astype(np.float32) for c in (19, 19, 38, 38))
+    ap, ah = post.flip_merge(bnh, bfh, bnp, bfp)
+    t = lambda a: np.ascontiguousarray(a.transpose(0, 3, 1, 2))
+    ap0, ah0 = post.flip_merge(t(bnh), t(bfh), t(bnp), t(bfp), layout=0)
+    for i in range(3):
+        wp, wh = glue_port.handle_paf_and_heat(bnh[i], bfh[i], bnp[i], bfp[i])
+        np.testing.assert_array_equal(ap[i], wp)
+        np.testing.assert_array_equal(ah[i], wh)
+        np.testing.assert_array_equal(ap0[i], wp.transpose(2, 0, 1))
+        np.testing.assert_array_equal(ah0[i], wh.transpose(2, 0, 1))
+
+
+def test_fused_flip_inference_matches_reference_shaped_composition(built, he_sd):
+    """PoseEngine.infer_batch(flip=True) on uint8 frames == per image: forward(img), forward(img[:, ::-1]) (fp32 parity
+    mode through the native net), the oracle's handle_paf_and_heat and paf_to_pose on the averaged maps."""
+    eng = pkg_module("engine")
+    nat = pkg_module("_native")
+    pe = eng.PoseEngine([v.numpy() for v in he_sd.values()], 0, mode="bf16", batch_cap=2, peak_cap=1024, human_cap=2048)
+    frames = np.random.RandomState(21).randint(0, 256, (2, 184, 248, 3)).astype(np.uint8)
+    fused = pe.infer_batch(frames, flip=True)
+    both = np.ascontiguousarray(np.concatenate([frames, frames[:, :, ::-1]], 0))
+    outs = [torch.empty((4, 38 if i % 2 == 0 else 19, 23, 31), device="cuda") for i in range(12)]
+    xd = torch.from_numpy(both).cuda()
+    pe.net.forward_u8_ptr(xd.data_ptr(), True, 4, 184, 248, pe.mode, [o.data_ptr() for o in outs], True,
+                          torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    paf = outs[10].permute(0, 2, 3, 1).contiguous().cpu().numpy()
+    heat = outs[11].permute(0, 2, 3, 1).contiguous().cpu().numpy()
+    port = pafprocess_oracle.load_port()
+    total = 0
+    for i in range(2):
+        ap, ah = glue_port.handle_paf_and_heat(heat[i], heat[2 + i], paf[i], paf[2 + i])
+        _, want = glue_port.paf_to_pose(ah, ap, port)
+        assert_humans_equal(fused[i], want, score_tol=0.0)
+        total += len(want)
+    plain = pe.infer_batch(frames)
+    assert total > 0 and any(len(a) != len(b) or a != b for a, b in zip(plain, fused))   # averaging changed something
+    assert nat.launch_count() > 0

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import POST_CASES, ROOT, assert_humans_equal, pkg_module
+from conftest import POST_CASES, ROOT, assert_humans_equal, golden, pkg_module
 from oracle import glue_port, net_port, nms_port, pafprocess_oracle, synth
 
 
@@ -105,6 +105,39 @@ def test_preprocess_and_flip_match_oracle():
     bp, bh = glue_port.handle_paf_and_heat(nh, fh, npf, fpf)
     np.testing.assert_array_equal(ap, bp)
     np.testing.assert_array_equal(ah, bh)
+
+
+def _flip_inputs():
+    """The seeded inputs tests/golden/make_golden.py fed to the reference's handle_paf_and_heat."""
+    return [np.random.RandomState(sd).rand(6, 5, c).astype(np.float32) for sd, c in ((1, 19), (2, 19), (3, 38), (4, 38))]
+
+
+def test_flip_merge_device_core_on_host_matches_reference_golden(built):
+    """csrc/tta_core.h (the functions the CUDA kernel calls) compiled for the host: bit-identical to the reference's
+    handle_paf_and_heat golden vector and to the oracle, in both layouts and for a batch."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "build", "libpostcore_host.so"))
+    lib.core_flip_merge.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 5
+
+    def run(normal, flipped, layout):
+        normal, flipped = np.ascontiguousarray(normal), np.ascontiguousarray(flipped)
+        out = np.empty_like(normal)
+        n, ch = normal.shape[0], (normal.shape[3] if layout == 1 else normal.shape[1])
+        h, w = (normal.shape[1:3] if layout == 1 else normal.shape[2:4])
+        assert lib.core_flip_merge(normal.ctypes.data, flipped.ctypes.data, out.ctypes.data, n, ch, h, w, layout) == 0
+        return out
+    nh, fh, npf, fpf = _flip_inputs()
+    f = golden("flip_merge")
+    np.testing.assert_array_equal(run(nh[None], fh[None], 1)[0], f["avg_heat"])
+    np.testing.assert_array_equal(run(npf[None], fpf[None], 1)[0], f["avg_paf"])
+    rs = np.random.RandomState(11)
+    bnh, bfh, bnp, bfp = (rs.randn(3, 7, 9, c).astype(np.float32) for c in (19, 19, 38, 38))
+    for i in range(3):
+        ap, ah = glue_port.handle_paf_and_heat(bnh[i], bfh[i], bnp[i], bfp[i])
+        np.testing.assert_array_equal(run(bnh, bfh, 1)[i], ah)
+        np.testing.assert_array_equal(run(bnp, bfp, 1)[i], ap)
+        # NCHW, the layout the fused path merges in
+        np.testing.assert_array_equal(run(bnh.transpose(0, 3, 1, 2), bfh.transpose(0, 3, 1, 2), 0)[i], ah.transpose(2, 0, 1))
+        np.testing.assert_array_equal(run(bnp.transpose(0, 3, 1, 2), bfp.transpose(0, 3, 1, 2), 0)[i], ap.transpose(2, 0, 1))
 
 
 @pytest.mark.parametrize("name", sorted(POST_CASES))
