@@ -110,7 +110,9 @@ def run_ours(args):
     # into the first convolution.  10 rotating device batches (10 x 13 MB > 126 MB L2) + 2 pinned host batches.
     g = torch.Generator().manual_seed(1234 + rank)
     host = [torch.randint(0, 256, (BATCH, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
-    devin = [torch.randint(0, 256, (BATCH, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for i in range(10)]
+    # enough rotating device batches that one full rotation exceeds the 126 MB L2 (10 at batch 32)
+    n_rot = max(10, -(-130_000_000 // (BATCH * H * W * 3)))
+    devin = [torch.randint(0, 256, (BATCH, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for i in range(n_rot)]
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
@@ -119,13 +121,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    infer_u8 = eng.infer_flip_async_u8 if args.flip else eng.infer_async_u8
+
     def step_device(i):
-        eng.infer_async_u8(devin[i % 10].data_ptr(), True, BATCH, H, W, 0.1, sptr)
+        infer_u8(devin[i % n_rot].data_ptr(), True, BATCH, H, W, 0.1, sptr)
 
     d2h_bytes = []
 
     def submit_e2e(i):
-        return eng.infer_async_u8(host[i % 2].data_ptr(), False, BATCH, H, W, 0.1, sptr)
+        return infer_u8(host[i % 2].data_ptr(), False, BATCH, H, W, 0.1, sptr)
 
     def fetch_e2e(ticket):
         eng.post.select(ticket)
@@ -218,18 +222,20 @@ def run_ours(args):
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "batch=32 per GPU, 368x368, rtpose VGG19 bf16 (tcgen05) + fused NMS/PAF-match/assembly "
-                               "(BASELINE.json configs[2]; configs[3] when n_gpus=8)",
+        "config": {"workload": "batch=%d per GPU, 368x368, rtpose VGG19 bf16 (tcgen05) + fused NMS/PAF-match/assembly%s"
+                               % (BATCH, " (BASELINE.json configs[2]; configs[3] when n_gpus=8)" if BATCH == 32 and not args.flip
+                                  else (", left/right flip test-time averaging on the device (2 forwards per frame)" if args.flip else "")),
                    "global_batch": BATCH * world, "weights": "He-normal seed 1234 (random init)",
                    "input": "uint8 HWC BGR frames, rtpose_preprocess fused on the device",
-                   "l2": "inputs rotate over 10 device batches (130 MB > 126 MB L2); ~1.4 GB of activations per step",
+                   "l2": "inputs rotate over %d device batches (%d MB > 126 MB L2); ~%d MB of activations per step"
+                         % (n_rot, n_rot * BATCH * H * W * 3 // 1000000, 44 * BATCH * (2 if args.flip else 1)),
                    "parallelism": "dp%d (frames sharded, one NCCL weight broadcast)" % world,
                    "post_status_bits": int(st0)},
         "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * H * W * world,
                 "d2h_bytes_per_step": (int(np.mean(d2h_bytes)) if d2h_bytes else 0) * world,   # rank 0's count x ranks
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "net_tflops_device": round(FLOPS_PER_FRAME * frames / (ms_dev * 1e-3) / 1e12 / world, 1),
+        "net_tflops_device": round(FLOPS_PER_FRAME * (2 if args.flip else 1) * frames / (ms_dev * 1e-3) / 1e12 / world, 1),
     }
     print(json.dumps(line))
     if world > 1:
@@ -319,8 +325,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step (the headline config is 32)")
+    ap.add_argument("--flip", action="store_true", help="left/right flip test-time averaging (2 forwards per frame)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global BATCH
+    BATCH = args.batch
     if args.impl == "reference":
         run_reference(args)
     else:
