@@ -225,50 +225,6 @@ struct SortShared {
     int bsf[kLimbWarps][32], bsl[kLimbWarps][32], bsd[kLimbWarps][32];
 };
 
-// Stable sort of up to two leaves (<= 16 keys each) by one warp: lanes 0-15 take leaf 0, lanes 16-31 leaf 1; every key's
-// final slot is its stable rank (#smaller + #equal-before), which is what insertion sort produces.
-__device__ __forceinline__ void warp_sort_two_leaves(uint64_t* v, long f0, long l0, long f1, long l1) {
-    const int lane = threadIdx.x & 31, h = lane >> 4, j = lane & 15;
-    const long f = h ? f1 : f0;
-    const int n = (int)(h ? l1 - f1 : l0 - f0);
-    const uint64_t key = (j < n) ? v[f + j] : ~0ull;
-    const uint32_t mh = (uint32_t)(key >> 32);
-    int rank = 0;
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const uint64_t other = __shfl_sync(0xffffffffu, key, (h << 4) | t);
-        const uint32_t oh = (uint32_t)(other >> 32);
-        if (t < n && (oh < mh || (oh == mh && t < j))) ++rank;
-    }
-    if (j < n) v[f + rank] = key;
-    __syncwarp();
-}
-
-// Exclusive scan of two counters at once (packed in one 64-bit word, counts < 2^31) + their totals.
-__device__ __forceinline__ void block_exclusive_scan2(int a, int b, int* offA, int* offB, int* totA, int* totB,
-                                                      unsigned long long* scratch /*[warps + 1]*/) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const unsigned long long v = ((unsigned long long)(unsigned)b << 32) | (unsigned)a;
-    unsigned long long inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) scratch[warp] = inc;
-    __syncthreads();
-    unsigned long long pre = 0, tot = 0;
-    for (int k = 0; k < nw; ++k) {
-        const unsigned long long c = scratch[k];
-        if (k < warp) pre += c;
-        tot += c;
-    }
-    const unsigned long long ex = pre + inc - v;
-    *offA = (int)(unsigned)ex; *offB = (int)(ex >> 32);
-    *totA = (int)(unsigned)tot; *totB = (int)(tot >> 32);
-    __syncthreads();
-}
-
 // Exact partition of v[f, l) with the rank-based formulation of the Hoare loop (post_core.h: lo-stop #k from the left
 // pairs with hi-stop #k from the right while posA[k] < posB[k]; cut = min(posA[K+1], posB[K])), evaluated ROW-WISE:
 // the range is cut into one contiguous segment per cooperating warp, inside a segment the 32 lanes take consecutive
