@@ -132,6 +132,29 @@ int b200pose_infer_u8_flip(b200pose_net* net, b200pose_post* post, const unsigne
                            int n, int H, int W, int mode, float thresh, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * 3c. Device-side crop_with_factor: replaces crop_with_factor / _factor_closest   lib/network/im_transform.py:113-134
+ *     (called by get_outputs, evaluate/coco_eval.py:87-91, with dest_size = cfg.DATASET.IMAGE_SIZE, factor =
+ *     cfg.MODEL.DOWNSAMPLE, is_ceil = True).  uint8 HWC BGR frames of ONE source size (a video stream, or one shape
+ *     bucket of a data set) -> cv2.resize(fx = fy = dest_size / min(h, w)) with OpenCV's 8-bit INTER_LINEAR arithmetic,
+ *     bit for bit (csrc/resize_core.h) -> zero padding bottom/right to a multiple of `factor` (a multiple of 8).
+ *   b200pose_crop_geometry         : host only; the values crop_with_factor returns / implies
+ *   b200pose_net_crop_with_factor  : images [n,src_h,src_w,3] -> out [n,pad_h,pad_w,3]; host or device pointers
+ *   b200pose_infer_raw_u8          : raw frames -> resize/pad -> network -> fused post-processing, all on the device;
+ *                                    flip != 0 adds left/right flip test-time averaging: the RAW frame is mirrored
+ *                                    before it is resized and padded, exactly like get_outputs(img[:, ::-1]) would see
+ *                                    it, then the maps are merged as handle_paf_and_heat does.
+ *     Person coordinates are in pixels of the padded frame (pad_h x pad_w), like the reference's.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b200pose_crop_geometry(int src_h, int src_w, int dest_size, int factor, double* im_scale, int* res_h, int* res_w,
+                           int* pad_h, int* pad_w);
+int b200pose_net_crop_with_factor(b200pose_net* net, const unsigned char* images, int images_on_device, int n, int src_h,
+                                  int src_w, int dest_size, int factor, unsigned char* out, int out_on_device,
+                                  void* cuda_stream);
+int b200pose_infer_raw_u8(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device, int n,
+                          int src_h, int src_w, int dest_size, int factor, int mode, float thresh, int flip,
+                          void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * 4. Legacy SWIG surface of lib/pafprocess (pafprocess.h:53-59, pafprocess.i:14): same names, same argument
  *    meaning; state is kept in a process-global context exactly like the reference's file-scope globals
  *    (pafprocess.cpp:12-13).  peaks [p1,p2,5] rows (x, y, score, id, part) sorted by part as paf_to_pose_cpp

@@ -56,6 +56,9 @@ def lib():
         "b200pose_flip_merge": ([vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp], ci),
         "b200pose_infer_flip": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
         "b200pose_infer_u8_flip": ([vp, vp, vp, ci, ci, ci, ci, ci, cf, vp], ci),
+        "b200pose_crop_geometry": ([ci, ci, ci, ci, ctypes.POINTER(ctypes.c_double)] + [ctypes.POINTER(ci)] * 4, ci),
+        "b200pose_net_crop_with_factor": ([vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp], ci),
+        "b200pose_infer_raw_u8": ([vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp], ci),
         "process_paf": ([ci, ci, ci, vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
         "get_num_humans": ([], ci),
         "get_part_cid": ([ci, ci], ci),
@@ -77,7 +80,8 @@ EXPORTED = ["b200pose_last_error", "b200pose_version", "b200pose_launch_count", 
             "b200pose_net_forward", "b200pose_net_forward_u8", "b200pose_net_profile", "b200pose_net_last_maps", "b200pose_post_create", "b200pose_post_destroy",
             "b200pose_post_run", "b200pose_post_sync", "b200pose_post_last_ticket", "b200pose_post_select", "b200pose_post_debug", "b200pose_post_num_humans", "b200pose_post_status",
             "b200pose_post_get_humans", "b200pose_post_get_peaks", "b200pose_infer", "b200pose_infer_u8", "b200pose_flip_merge", "b200pose_infer_flip",
-            "b200pose_infer_u8_flip", "process_paf", "get_num_humans",
+            "b200pose_infer_u8_flip", "b200pose_crop_geometry", "b200pose_net_crop_with_factor",
+            "b200pose_infer_raw_u8", "process_paf", "get_num_humans",
             "get_part_cid", "get_score", "get_part_x", "get_part_y", "get_part_score"]
 
 
@@ -85,6 +89,16 @@ def check(rc, what=""):
     if rc != 0:
         msg = lib().b200pose_last_error()
         raise B200PoseError("%s failed (rc=%d): %s" % (what or "b200pose call", rc, msg.decode() if msg else "?"))
+
+
+def crop_geometry(src_h, src_w, dest_size=368, factor=8):
+    """(im_scale, (res_h, res_w), (pad_h, pad_w)) exactly as crop_with_factor (im_transform.py:119-134) computes them.
+    Host arithmetic only, but it lives in the library so that there is one implementation."""
+    sc = ctypes.c_double()
+    v = [ctypes.c_int() for _ in range(4)]
+    check(lib().b200pose_crop_geometry(int(src_h), int(src_w), int(dest_size), int(factor), ctypes.byref(sc),
+                                       *[ctypes.byref(x) for x in v]), "b200pose_crop_geometry")
+    return sc.value, (v[0].value, v[1].value), (v[2].value, v[3].value)
 
 
 def launch_count():

@@ -14,6 +14,7 @@
 #include "conv_misc.cuh"
 #include "conv_tc.cuh"
 #include "postprocess.cuh"
+#include "resize.cuh"
 #include "tta.cuh"
 
 using namespace b2p;
@@ -148,6 +149,7 @@ struct b200pose_net {
     const void* last_in = nullptr;    // device pointer of the last forward's input (profiling hook)
     int last_in_u8 = 0;
     DevBuf<unsigned char> in_stage_u8;
+    DevBuf<unsigned char> raw_stage;   // raw (un-resized) frames of b200pose_*crop* / b200pose_infer_raw_u8
 };
 
 struct b200pose_post {
@@ -431,6 +433,7 @@ void b200pose_net_destroy(b200pose_net* net) {
     for (auto* b : lb) b->release();
     DevBuf<float>* fb[] = {&net->in_stage, &net->f_a, &net->f_b, &net->f_cat, &net->f_x, &net->f_y, &net->f_in, &net->f_u8};
     net->in_stage_u8.release();
+    net->raw_stage.release();
     for (auto* b : fb) b->release();
     for (auto& b : net->out_f32) b.release();
     delete net;
@@ -863,6 +866,101 @@ int b200pose_infer_flip(b200pose_net* net, b200pose_post* post, const float* inp
 int b200pose_infer_u8_flip(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device,
                            int n, int H, int W, int mode, float thresh, void* cuda_stream) {
     return infer_flip_impl(net, post, images, 1, input_on_device, n, H, W, mode, thresh, cuda_stream);
+}
+
+// ------------------------------------------------------------------------------------------------ crop_with_factor
+static int crop_check(int n, int src_h, int src_w, int dest_size, int factor, CropGeom* g) {
+    if (n < 1 || src_h < 1 || src_w < 1 || dest_size < 1) return fail("crop_with_factor: bad shape");
+    if (factor < 8 || factor % 8) return fail("crop_with_factor: factor must be a multiple of 8 (the network's stride)");
+    *g = crop_geometry(src_h, src_w, dest_size, factor);
+    if (g->res_h < 1 || g->res_w < 1) return fail("crop_with_factor: the resized frame would be empty");
+    if ((long)g->pad_h * g->pad_w > (1L << 28)) return fail("crop_with_factor: resized frame too large");
+    return 0;
+}
+
+int b200pose_crop_geometry(int src_h, int src_w, int dest_size, int factor, double* im_scale, int* res_h, int* res_w,
+                           int* pad_h, int* pad_w) {
+    CropGeom g;
+    if (int rc = crop_check(1, src_h, src_w, dest_size, factor, &g)) return rc;
+    if (im_scale) *im_scale = g.im_scale;
+    if (res_h) *res_h = g.res_h;
+    if (res_w) *res_w = g.res_w;
+    if (pad_h) *pad_h = g.pad_h;
+    if (pad_w) *pad_w = g.pad_w;
+    return 0;
+}
+
+int b200pose_net_crop_with_factor(b200pose_net* net, const unsigned char* images, int images_on_device, int n, int src_h,
+                                  int src_w, int dest_size, int factor, unsigned char* out, int out_on_device,
+                                  void* cuda_stream) {
+    if (!net) return fail("null net");
+    if (!images || !out) return fail("crop_with_factor: null pointer");
+    CropGeom g;
+    if (int rc = crop_check(n, src_h, src_w, dest_size, factor, &g)) return rc;
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const size_t raw = (size_t)n * src_h * src_w * 3, outb = (size_t)n * g.pad_h * g.pad_w * 3;
+    const unsigned char* d_in = images;
+    if (!images_on_device) {
+        CU(net->raw_stage.ensure(raw));
+        CU(cudaMemcpyAsync(net->raw_stage.p, images, raw, cudaMemcpyHostToDevice, st));
+        d_in = net->raw_stage.p;
+    }
+    unsigned char* d_out = out;
+    if (!out_on_device) {
+        CU(net->in_stage_u8.ensure(outb));
+        d_out = net->in_stage_u8.p;
+    }
+    cudaError_t e = crop_with_factor_launch(d_in, d_out, n, src_h, src_w, g, st);
+    if (e != cudaSuccess) return fail("crop_with_factor_launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    if (!out_on_device) CU(cudaMemcpyAsync(out, d_out, outb, cudaMemcpyDeviceToHost, st));
+    if (!images_on_device || !out_on_device) CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200pose_infer_raw_u8(b200pose_net* net, b200pose_post* post, const unsigned char* images, int input_on_device, int n,
+                          int src_h, int src_w, int dest_size, int factor, int mode, float thresh, int flip,
+                          void* cuda_stream) {
+    if (!net || !post) return fail("null handle");
+    if (!net->finalized) return fail("net not finalized");
+    if (net->device != post->device) return fail("net and post live on different devices");
+    if (!images) return fail("infer_raw: null pointer");
+    if (n > post->pb.batch_cap) return fail("batch %d exceeds post batch_cap %d", n, post->pb.batch_cap);
+    CropGeom g;
+    if (int rc = crop_check(n, src_h, src_w, dest_size, factor, &g)) return rc;
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const int nimg = flip ? 2 * n : n, H = g.pad_h, W = g.pad_w;
+    const size_t raw = (size_t)n * src_h * src_w * 3;
+    // the caller keeps a host input alive until b200pose_post_sync(), as for b200pose_infer
+    const unsigned char* d_raw = images;
+    if (!input_on_device || flip) {
+        CU(net->raw_stage.ensure(raw * (flip ? 2 : 1)));
+        CU(cudaMemcpyAsync(net->raw_stage.p, images, raw, input_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        d_raw = net->raw_stage.p;
+    }
+    cudaError_t e;
+    if (flip) {   // mirrored RAW frames: the padding of both orientations ends up on the right, as for the reference
+        e = tta_mirror_u8hwc(net->raw_stage.p, net->raw_stage.p + raw, n, src_h, src_w, st);
+        if (e != cudaSuccess) return fail("tta_mirror: %s", cudaGetErrorString(e));
+        ++g_launches;
+    }
+    CU(net->in_stage_u8.ensure((size_t)nimg * H * W * 3));
+    e = crop_with_factor_launch(d_raw, net->in_stage_u8.p, nimg, src_h, src_w, g, st);
+    if (e != cudaSuccess) return fail("crop_with_factor_launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    int rc = net_forward_impl(net, net->in_stage_u8.p, 1, 1, nimg, H, W, mode, nullptr, 1, st, false);
+    if (rc) return rc;
+    const int h = H / 8, w = W / 8;
+    if (!flip) return post_run_dev(post, net->out_f32[11].p, net->out_f32[10].p, 0, n, h, w, thresh, st);
+    const size_t eh = (size_t)n * kHeat * h * w, ep = (size_t)n * kPaf * h * w;
+    CU(post->d_heat.ensure(eh));
+    CU(post->d_paf.ensure(ep));
+    rc = flip_merge_dev(net->out_f32[11].p, net->out_f32[11].p + eh, net->out_f32[10].p, net->out_f32[10].p + ep, 0, n, h,
+                        w, post->d_heat.p, post->d_paf.p, st);
+    if (rc) return rc;
+    return post_run_dev(post, post->d_heat.p, post->d_paf.p, 0, n, h, w, thresh, st);
 }
 
 // ------------------------------------------------------------------------------------------------ legacy pafprocess

@@ -40,6 +40,23 @@ class NativeNet:
                                                     arr, int(out_on_device), ctypes.c_void_p(stream)),
                   "b200pose_net_forward_u8")
 
+    def crop_with_factor(self, images, dest_size=368, factor=8):
+        """Device-side crop_with_factor (im_transform.py:119-134) of uint8 BGR frames of one size: [n,h,w,3] or [h,w,3]
+        -> (padded frames, im_scale, resized shape) like the reference (which returns them for one image)."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        single = images.ndim == 3
+        if single:
+            images = images[None]
+        n, sh, sw, c = images.shape
+        if c != 3:
+            raise nat.B200PoseError("crop_with_factor: expected 3-channel BGR frames")
+        scale, (rh, rw), (ph, pw) = nat.crop_geometry(sh, sw, dest_size, factor)
+        out = np.empty((n, ph, pw, 3), np.uint8)
+        nat.check(nat.lib().b200pose_net_crop_with_factor(self._h, ctypes.c_void_p(images.ctypes.data), 0, n, sh, sw,
+                                                          int(dest_size), int(factor), ctypes.c_void_p(out.ctypes.data), 0,
+                                                          None), "b200pose_net_crop_with_factor")
+        return (out[0] if single else out), scale, (rh, rw, 3)
+
     def __del__(self):
         try:
             if self._h:
@@ -187,6 +204,38 @@ class PoseEngine:
                   "b200pose_infer_u8_flip")
         self._last = (n, H, W)
         return self.post.last_ticket()
+
+    def infer_raw_async_u8(self, in_ptr, in_on_device, n, src_h, src_w, dest_size=368, factor=8, thresh=0.1, flip=False,
+                           stream=0):
+        """Raw uint8 BGR frames of one size [n,src_h,src_w,3]: crop_with_factor (resize + pad), the network and the
+        post-processing all run on the device.  Person coordinates refer to the padded frame."""
+        nat.check(nat.lib().b200pose_infer_raw_u8(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n,
+                                                  src_h, src_w, int(dest_size), int(factor), self.mode,
+                                                  ctypes.c_float(thresh), int(bool(flip)), ctypes.c_void_p(stream)),
+                  "b200pose_infer_raw_u8")
+        _, _, (ph, pw) = nat.crop_geometry(src_h, src_w, dest_size, factor)
+        self._last = (n, ph, pw)
+        return self.post.last_ticket()
+
+    def infer_images(self, images, dest_size=368, factor=8, thresh=0.1, flip=False):
+        """images: a list of raw uint8 BGR frames of arbitrary (mixed) sizes, as cv2.imread returns them.  Frames are
+        bucketed by shape (one launch sequence per bucket, at most batch_cap frames each); returns per-image human lists
+        in input order, coordinates normalised to the padded frame like paf_to_pose_cpp's."""
+        buckets = {}
+        for i, im in enumerate(images):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise nat.B200PoseError("infer_images: expected uint8 [h,w,3] frames")
+            buckets.setdefault(im.shape[:2], []).append(i)
+        out = [None] * len(images)
+        for (sh, sw), idx in buckets.items():
+            for k in range(0, len(idx), self.post.batch_cap):
+                part = idx[k:k + self.post.batch_cap]
+                batch = np.ascontiguousarray(np.stack([images[i] for i in part]))
+                self._keep = batch
+                self.infer_raw_async_u8(batch.ctypes.data, False, len(part), sh, sw, dest_size, factor, thresh, flip)
+                for i, humans in zip(part, self.fetch()):
+                    out[i] = humans
+        return out
 
     def fetch(self, check=True, ticket=None):
         """Results of run `ticket` (default: the latest).  Up to two runs may be in flight: submit i+1, then fetch i."""

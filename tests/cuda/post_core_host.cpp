@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/post_core.h"
+#include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/resize_core.h"
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/tta_core.h"
 
 using namespace b2p;
@@ -140,4 +141,17 @@ extern "C" int core_flip_merge(const float* normal, const float* flipped, float*
                     out[i * per + c * sc + y * sy + x * sx] =
                         tta_flip_merge_at(normal + i * per, flipped + i * per, paf, c, y, x, w, sc, sy, sx);
     return bad;
+}
+
+// crop_with_factor with the exact functions the CUDA kernel calls (csrc/resize_core.h).  geom: im_scale, res_h, res_w,
+// pad_h, pad_w, area2.  out (may be NULL to query the geometry only): uint8 [pad_h, pad_w, 3].
+extern "C" int core_crop_with_factor(const unsigned char* src, int src_h, int src_w, int dest_size, int factor,
+                                     unsigned char* out, double* geom) {
+    const CropGeom g = crop_geometry(src_h, src_w, dest_size, factor);
+    geom[0] = g.im_scale; geom[1] = g.res_h; geom[2] = g.res_w; geom[3] = g.pad_h; geom[4] = g.pad_w; geom[5] = g.area2;
+    if (!out) return 0;
+    for (int y = 0; y < g.pad_h; ++y)
+        for (int x = 0; x < g.pad_w; ++x)
+            for (int c = 0; c < 3; ++c) out[((long)y * g.pad_w + x) * 3 + c] = crop_px(src, src_h, src_w, 3, g, y, x, c);
+    return 0;
 }

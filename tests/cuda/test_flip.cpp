@@ -1,5 +1,5 @@
-// TEST INFRASTRUCTURE: standalone check of the flip test-time-averaging entry points through the C ABI only
-// (host pointers; no torch, starts in a second).  The fused b200pose_infer*_flip calls are compared bit for bit with
+// TEST INFRASTRUCTURE: standalone check of the flip test-time-averaging and crop_with_factor entry points through the
+// C ABI only (host pointers; no torch, starts in a second).  The fused b200pose_infer*_flip calls are compared bit for bit with
 // the composition of already-validated calls: forward(frames) + forward(host-mirrored frames) + host merge with
 // csrc/tta_core.h + b200pose_post_run.
 // Build: g++ -O2 -std=c++17 tests/cuda/test_flip.cpp -o build/test_flip -L<pkg> -lb200pose -Wl,-rpath,<pkg>
@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/b200pose.h"
+#include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/resize_core.h"
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/tta_core.h"
 
 static uint64_t g_state = 0x9E3779B97F4A7C15ull;
@@ -44,6 +45,93 @@ static bool same(const std::vector<std::vector<float>>& a, const std::vector<std
     for (size_t i = 0; i < a.size(); ++i)
         if (a[i].size() != b[i].size() || (a[i].size() && memcmp(a[i].data(), b[i].data(), a[i].size() * 4))) return false;
     return true;
+}
+
+// host crop_with_factor with the shared core (the kernel's own functions compiled for the host)
+static std::vector<unsigned char> host_crop(const std::vector<unsigned char>& raw, int n, int sh, int sw, int dest, int factor,
+                                            b2p::CropGeom* geom) {
+    const b2p::CropGeom g = b2p::crop_geometry(sh, sw, dest, factor);
+    *geom = g;
+    std::vector<unsigned char> out((size_t)n * g.pad_h * g.pad_w * 3);
+    for (int i = 0; i < n; ++i)
+        for (int y = 0; y < g.pad_h; ++y)
+            for (int x = 0; x < g.pad_w; ++x)
+                for (int c = 0; c < 3; ++c)
+                    out[(((size_t)i * g.pad_h + y) * g.pad_w + x) * 3 + c] =
+                        b2p::crop_px(raw.data() + (size_t)i * sh * sw * 3, sh, sw, 3, g, y, x, c);
+    return out;
+}
+
+static int raw_section(b200pose_net* net, b200pose_post* post) {
+    int failures = 0;
+    const int n = 2;
+    // 1. the crop kernel alone: general bilinear (up- and down-scaling), the exact-2x INTER_AREA switch, a cut 2x box
+    const int shapes[5][3] = {{150, 211, 184}, {480, 640, 368}, {368, 400, 184}, {368, 403, 184}, {97, 64, 200}};
+    for (auto& sp : shapes) {
+        const int sh = sp[0], sw = sp[1], dest = sp[2];
+        std::vector<unsigned char> raw((size_t)n * sh * sw * 3);
+        for (auto& b : raw) b = (unsigned char)(rnd() & 255);
+        b2p::CropGeom g;
+        const std::vector<unsigned char> want = host_crop(raw, n, sh, sw, dest, 8, &g);
+        double sc; int rh, rw, ph, pw;
+        CHECK(b200pose_crop_geometry(sh, sw, dest, 8, &sc, &rh, &rw, &ph, &pw));
+        std::vector<unsigned char> got(want.size(), 0xAA);
+        CHECK(b200pose_net_crop_with_factor(net, raw.data(), 0, n, sh, sw, dest, 8, got.data(), 0, nullptr));
+        const bool ok = sc == g.im_scale && rh == g.res_h && rw == g.res_w && ph == g.pad_h && pw == g.pad_w && got == want;
+        printf("%s  crop_with_factor kernel %dx%d -> %dx%d (pad %dx%d%s) vs host core\n", ok ? "PASS" : "FAIL", sh, sw, rh, rw,
+               ph, pw, g.area2 ? ", 2x area" : "");
+        failures += !ok;
+    }
+    // 2. fused raw path == host crop + the validated uint8 entry points, without and with flip averaging
+    const int sh = 150, sw = 211, dest = 184;
+    std::vector<unsigned char> raw((size_t)n * sh * sw * 3), raw_m(raw.size());
+    for (auto& b : raw) b = (unsigned char)(rnd() & 255);
+    for (int i = 0; i < n; ++i)
+        for (int y = 0; y < sh; ++y)
+            for (int x = 0; x < sw; ++x)
+                for (int c = 0; c < 3; ++c)
+                    raw_m[(((size_t)i * sh + y) * sw + x) * 3 + c] = raw[(((size_t)i * sh + y) * sw + (sw - 1 - x)) * 3 + c];
+    b2p::CropGeom g;
+    const std::vector<unsigned char> fr = host_crop(raw, n, sh, sw, dest, 8, &g), fr_m = host_crop(raw_m, n, sh, sw, dest, 8, &g);
+    const int H = g.pad_h, W = g.pad_w, h = H / 8, w = W / 8;
+    std::vector<std::vector<float>> want, got;
+    CHECK(b200pose_infer_u8(net, post, fr.data(), 0, n, H, W, 0, 0.1f, nullptr));
+    if (fetch(post, n, want)) return failures + 1;
+    CHECK(b200pose_infer_raw_u8(net, post, raw.data(), 0, n, sh, sw, dest, 8, 0, 0.1f, 0, nullptr));
+    if (fetch(post, n, got)) return failures + 1;
+    size_t persons = 0;
+    for (auto& r : want) persons += r.size() / B200POSE_HUMAN_FLOATS;
+    bool ok = same(want, got);
+    printf("%s  b200pose_infer_raw_u8 == host crop + b200pose_infer_u8 [%dx%d -> %dx%d, %zu persons]\n", ok ? "PASS" : "FAIL", sh,
+           sw, H, W, persons);
+    failures += !ok;
+    const size_t eh = (size_t)n * 19 * h * w, ep = (size_t)n * 38 * h * w;
+    std::vector<float> paf_n(ep), heat_n(eh), paf_f(ep), heat_f(eh), avg_p(ep), avg_h(eh);
+    float* outs[12] = {nullptr};
+    outs[10] = paf_n.data(); outs[11] = heat_n.data();
+    CHECK(b200pose_net_forward_u8(net, fr.data(), 0, n, H, W, 0, outs, 0, nullptr));
+    outs[10] = paf_f.data(); outs[11] = heat_f.data();
+    CHECK(b200pose_net_forward_u8(net, fr_m.data(), 0, n, H, W, 0, outs, 0, nullptr));
+    for (int i = 0; i < n; ++i)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                for (int c = 0; c < 19; ++c)
+                    avg_h[(size_t)i * 19 * h * w + ((size_t)c * h + y) * w + x] = b2p::tta_flip_merge_at(
+                        heat_n.data() + (size_t)i * 19 * h * w, heat_f.data() + (size_t)i * 19 * h * w, false, c, y, x, w,
+                        (long)h * w, w, 1);
+                for (int c = 0; c < 38; ++c)
+                    avg_p[(size_t)i * 38 * h * w + ((size_t)c * h + y) * w + x] = b2p::tta_flip_merge_at(
+                        paf_n.data() + (size_t)i * 38 * h * w, paf_f.data() + (size_t)i * 38 * h * w, true, c, y, x, w,
+                        (long)h * w, w, 1);
+            }
+    CHECK(b200pose_post_run(post, avg_h.data(), avg_p.data(), 0, 0, n, h, w, 0.1f, nullptr));
+    if (fetch(post, n, want)) return failures + 1;
+    CHECK(b200pose_infer_raw_u8(net, post, raw.data(), 0, n, sh, sw, dest, 8, 0, 0.1f, 1, nullptr));
+    if (fetch(post, n, got)) return failures + 1;
+    ok = same(want, got);
+    printf("%s  b200pose_infer_raw_u8(flip) == mirror raw + host crop + forward x2 + merge + post\n", ok ? "PASS" : "FAIL");
+    failures += !ok;
+    return failures;
 }
 
 int main(int argc, char** argv) {
@@ -151,6 +239,7 @@ int main(int argc, char** argv) {
             printf("%s  averaged result differs from the single-orientation result\n", same(want, plain) ? "WARN" : "PASS");
         }
     }
+    failures += raw_section(net, post);
     b200pose_post_destroy(post);
     b200pose_net_destroy(net);
     printf("%s (%d failures), kernels launched: %ld\n", failures ? "FLIP TEST FAILED" : "FLIP TEST OK", failures,

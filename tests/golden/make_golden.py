@@ -14,6 +14,8 @@ import os
 import sys
 import types
 
+ARGS = sys.argv[1:]     # optional: "crop" regenerates only the crop_with_factor fixture
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -83,9 +85,31 @@ def import_reference():
     return get_model, ref_p2p, ref_eval, cfg
 
 
+CROP_CASES = (("50x61", 50, 61, 96, 5), ("64x71_half", 64, 71, 32, 6), ("30x22_up", 30, 22, 40, 7))
+
+
+def make_crop():
+    """crop_with_factor (lib/network/im_transform.py:119-134) of the reference on seeded uint8 frames: general bilinear
+    down-scaling, an exact 2x reduction with a cut last column (cv2 switches to INTER_AREA), up-scaling."""
+    from lib.network import im_transform as ref_tf
+    out = {}
+    for name, h, w, dest, seed in CROP_CASES:
+        img = np.random.RandomState(seed).randint(0, 256, (h, w, 3)).astype(np.uint8)
+        croped, scale, shape = ref_tf.crop_with_factor(img, dest, factor=8, is_ceil=True)
+        out[name + "_out"] = croped
+        out[name + "_meta"] = np.array([scale, shape[0], shape[1]], np.float64)
+        out[name + "_digest"] = digest(img)
+        print("crop", name, img.shape, "->", shape, croped.shape, scale)
+    np.savez_compressed(os.path.join(OUT, "crop_with_factor.npz"), **out)
+
+
 def main():
     import torch
     get_model, ref_p2p, ref_eval, cfg = import_reference()
+    if not ARGS or "crop" in ARGS:
+        make_crop()
+        if ARGS == ["crop"]:
+            return
     torch.manual_seed(0)
 
     # ---------------- network (rtpose_model.forward) ----------------

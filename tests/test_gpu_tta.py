@@ -1,5 +1,6 @@
-"""GPU (-m gpu): flip test-time averaging on the device against the oracle's
-handle_paf_and_heat, the reference's golden vector and the reference-shaped composition
+"""GPU (-m gpu): the widened rows of SURVEY.md 8(f) - device-side crop_with_factor (rank 1) and flip test-time
+averaging (8(a) F1 / rank 2) - against the oracle (cv2-based crop_with_factor, handle_paf_and_heat), the reference's
+golden vectors and the reference-shaped composition
 get_outputs(img) + get_outputs(img[:, ::-1]) + handle_paf_and_heat + paf_to_pose."""
 import os
 import subprocess
@@ -16,7 +17,8 @@ pytestmark = pytest.mark.gpu
 
 def test_flip_harness_through_the_c_abi(built):
     """tests/cuda/test_flip.cpp: fused b200pose_infer*_flip == forward x2 + host merge + post_run, bit for bit, in all
-    three arithmetic modes; merge kernel == host core in both layouts."""
+    three arithmetic modes; merge kernel == host core in both layouts; crop_with_factor kernel == host core;
+    b200pose_infer_raw_u8 (with and without flip) == host crop + the uint8 entry points."""
     r = subprocess.run([os.path.join(ROOT, "build", "test_flip"), "184", "248"], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=300)
     print(r.stdout)
@@ -74,3 +76,48 @@ def test_fused_flip_inference_matches_reference_shaped_composition(built, he_sd)
     plain = pe.infer_batch(frames)
     assert total > 0 and any(len(a) != len(b) or a != b for a, b in zip(plain, fused))   # averaging changed something
     assert nat.launch_count() > 0
+
+
+def test_crop_with_factor_kernel_matches_reference_golden_and_cv2(built, he_sd):
+    eng = pkg_module("engine")
+    net = eng.NativeNet(0)                      # crop_with_factor needs no weights
+    f = golden("crop_with_factor")              # produced by the reference's crop_with_factor
+    for name, h, w, dest, seed in (("50x61", 50, 61, 96, 5), ("64x71_half", 64, 71, 32, 6), ("30x22_up", 30, 22, 40, 7)):
+        img = np.random.RandomState(seed).randint(0, 256, (h, w, 3)).astype(np.uint8)
+        out, scale, shape = net.crop_with_factor(img, dest, 8)
+        np.testing.assert_array_equal(out, f[name + "_out"])
+        assert [scale, shape[0], shape[1]] == list(f[name + "_meta"])
+    rs = np.random.RandomState(4)
+    for (h, w, dest) in ((200, 230, 368), (480, 640, 368), (736, 739, 368), (1080, 1920, 368), (97, 64, 200), (368, 368, 368)):
+        frames = rs.randint(0, 256, (2, h, w, 3)).astype(np.uint8)
+        out, scale, shape = net.crop_with_factor(frames, dest, 8)
+        for i in range(2):
+            want, ws, wshape = glue_port.crop_with_factor(frames[i], dest, 8)       # cv2.resize on the host
+            assert scale == ws and shape == tuple(wshape)
+            np.testing.assert_array_equal(out[i], want)
+
+
+def test_raw_frames_of_mixed_sizes_match_reference_shaped_pipeline(built, he_sd):
+    """PoseEngine.infer_images (device crop_with_factor + net + post, frames bucketed by shape) == per image: the
+    oracle's crop_with_factor (cv2), the native uint8 forward, the oracle's paf_to_pose."""
+    eng = pkg_module("engine")
+    pe = eng.PoseEngine([v.numpy() for v in he_sd.values()], 0, mode="bf16", batch_cap=2, peak_cap=1024, human_cap=2048)
+    rs = np.random.RandomState(31)
+    imgs = [rs.randint(0, 256, s).astype(np.uint8) for s in ((150, 211, 3), (120, 100, 3), (150, 211, 3))]
+    got = pe.infer_images(imgs, dest_size=184, factor=8)
+    port = pafprocess_oracle.load_port()
+    total = 0
+    for i, im in enumerate(imgs):
+        crop, _, _ = glue_port.crop_with_factor(im, 184, 8)
+        H, W = crop.shape[:2]
+        outs = [torch.empty((1, 38 if k % 2 == 0 else 19, H // 8, W // 8), device="cuda") for k in range(12)]
+        xd = torch.from_numpy(np.ascontiguousarray(crop[None])).cuda()
+        pe.net.forward_u8_ptr(xd.data_ptr(), True, 1, H, W, pe.mode, [o.data_ptr() for o in outs], True,
+                              torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        heat = outs[11][0].permute(1, 2, 0).contiguous().cpu().numpy()
+        paf = outs[10][0].permute(1, 2, 0).contiguous().cpu().numpy()
+        _, want = glue_port.paf_to_pose(heat, paf, port)
+        assert_humans_equal(got[i], want, score_tol=0.0)
+        total += len(want)
+    assert total > 0

@@ -140,6 +140,109 @@ def test_flip_merge_device_core_on_host_matches_reference_golden(built):
         np.testing.assert_array_equal(run(bnp.transpose(0, 3, 1, 2), bfp.transpose(0, 3, 1, 2), 0)[i], ap.transpose(2, 0, 1))
 
 
+def _host_crop(lib, img, dest, factor=8):
+    img = np.ascontiguousarray(img)
+    g = np.zeros(6)
+    lib.core_crop_with_factor(img.ctypes.data, img.shape[0], img.shape[1], dest, factor, None, g.ctypes.data)
+    out = np.empty((int(g[3]), int(g[4]), 3), np.uint8)
+    lib.core_crop_with_factor(img.ctypes.data, img.shape[0], img.shape[1], dest, factor, out.ctypes.data, g.ctypes.data)
+    return out, float(g[0]), (int(g[1]), int(g[2]), 3)
+
+
+def _core_lib():
+    lib = ctypes.CDLL(os.path.join(ROOT, "build", "libpostcore_host.so"))
+    lib.core_crop_with_factor.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 2
+    return lib
+
+
+def test_crop_with_factor_device_core_on_host_matches_reference_golden_and_cv2(built):
+    """csrc/resize_core.h (the functions the CUDA kernel calls) compiled for the host == the reference's
+    crop_with_factor golden vectors and == cv2.resize-based oracle on random shapes, bit for bit (incl. the exact-2x
+    INTER_AREA switch with a cut last box, up-scaling, 1-pixel-wide frames)."""
+    lib = _core_lib()
+    f = golden("crop_with_factor")
+    for name, h, w, dest, seed in (("50x61", 50, 61, 96, 5), ("64x71_half", 64, 71, 32, 6), ("30x22_up", 30, 22, 40, 7)):
+        img = np.random.RandomState(seed).randint(0, 256, (h, w, 3)).astype(np.uint8)
+        out, scale, shape = _host_crop(lib, img, dest)
+        np.testing.assert_array_equal(out, f[name + "_out"])
+        assert [scale, shape[0], shape[1]] == list(f[name + "_meta"])
+    rs = np.random.RandomState(3)
+    shapes = [(int(rs.randint(8, 500)), int(rs.randint(8, 500))) for _ in range(40)]
+    shapes += [(736, 739), (739, 736), (737, 736), (368, 368), (368, 392), (480, 640), (2, 3), (1, 7), (9, 1)]
+    for (h, w) in shapes:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        dest = int(rs.choice([184, 368, 552]))
+        want, ws, wshape = glue_port.crop_with_factor(img, dest, 8)
+        out, scale, shape = _host_crop(lib, img, dest)
+        assert out.shape == want.shape and scale == ws and shape == tuple(wshape), (h, w, dest)
+        np.testing.assert_array_equal(out, want)
+
+
+def test_crop_geometry_and_python_wrappers_without_a_gpu(built, monkeypatch):
+    """b200pose_crop_geometry is host arithmetic (callable without a GPU).  The Python wrappers around the device entry
+    points (NativeNet.crop_with_factor, PoseEngine.infer_images' shape bucketing) are exercised against a stand-in
+    library whose device calls are emulated with the host build of the same core."""
+    nat = pkg_module("_native")
+    eng = pkg_module("engine")
+    for (h, w, dest) in ((200, 230, 368), (368, 368, 368), (736, 739, 368), (1080, 1920, 368), (97, 64, 200)):
+        img = np.zeros((h, w, 3), np.uint8)
+        want, ws, wshape = glue_port.crop_with_factor(img, dest, 8)
+        scale, res, pad = nat.crop_geometry(h, w, dest, 8)
+        assert scale == ws and res == tuple(wshape[:2]) and pad == want.shape[:2]
+    with pytest.raises(nat.B200PoseError):
+        nat.crop_geometry(100, 100, 368, 12)          # factor must be a multiple of the network stride
+    core, real = _core_lib(), nat.lib()
+    calls = []
+
+    class Fake:
+        b200pose_crop_geometry = staticmethod(real.b200pose_crop_geometry)
+        b200pose_last_error = staticmethod(real.b200pose_last_error)
+
+        @staticmethod
+        def b200pose_net_crop_with_factor(h, images, on_dev, n, sh, sw, dest, factor, out, out_on_dev, stream):
+            g = np.zeros(6)
+            for i in range(n):
+                core.core_crop_with_factor(images.value + i * sh * sw * 3, sh, sw, dest, factor, None, g.ctypes.data)
+                core.core_crop_with_factor(images.value + i * sh * sw * 3, sh, sw, dest, factor,
+                                           out.value + i * int(g[3]) * int(g[4]) * 3, g.ctypes.data)
+            return 0
+
+        @staticmethod
+        def b200pose_infer_raw_u8(net, post, images, on_dev, n, sh, sw, dest, factor, mode, thresh, flip, stream):
+            first = np.ctypeslib.as_array(ctypes.cast(images.value, ctypes.POINTER(ctypes.c_ubyte)), (n, sh, sw, 3))[:, 0, 0, 0]
+            calls.append((n, sh, sw, flip, [int(v) for v in first]))
+            return 0
+
+    monkeypatch.setattr(nat, "lib", lambda: Fake)
+    net = object.__new__(eng.NativeNet)
+    net._h = None
+    rs = np.random.RandomState(8)
+    frames = rs.randint(0, 256, (3, 120, 90, 3)).astype(np.uint8)
+    out, scale, shape = net.crop_with_factor(frames, 184, 8)
+    for i in range(3):
+        want, ws, wshape = glue_port.crop_with_factor(frames[i], 184, 8)
+        np.testing.assert_array_equal(out[i], want)
+        assert scale == ws and shape == tuple(wshape)
+    one, _, _ = net.crop_with_factor(frames[1], 184, 8)
+    np.testing.assert_array_equal(one, out[1])
+
+    class StubPost:
+        batch_cap = 2
+        def last_ticket(self): return 0
+    pe = object.__new__(eng.PoseEngine)
+    pe.net, pe.post, pe.mode = net, StubPost(), 0
+    pe.net._h = pe.post._h = None
+    pe.fetch = lambda: [("humans-of", v) for v in calls[-1][4]]
+    imgs = [np.full((40, 50, 3), 1, np.uint8), np.full((30, 50, 3), 2, np.uint8), np.full((40, 50, 3), 3, np.uint8),
+            np.full((40, 50, 3), 4, np.uint8), np.full((30, 50, 3), 5, np.uint8)]
+    res = pe.infer_images(imgs, dest_size=64, flip=True)
+    assert res == [("humans-of", i + 1) for i in range(5)]                         # input order is restored
+    assert [(c[0], c[1], c[2], c[3]) for c in calls] == [(2, 40, 50, 1), (1, 40, 50, 1), (2, 30, 50, 1)]   # <= batch_cap
+    assert pe._last == (2, 64, 112)                                               # padded size of the last bucket (30x50 -> 64x107)
+    with pytest.raises(nat.B200PoseError):
+        pe.infer_images([np.zeros((4, 4), np.uint8)])
+
+
 @pytest.mark.parametrize("name", sorted(POST_CASES))
 def test_device_cores_on_host_match_oracle(name, built):
     """csrc/post_core.h (pair scoring, std::sort emulation, greedy matching, indexed person assembly) compiled
