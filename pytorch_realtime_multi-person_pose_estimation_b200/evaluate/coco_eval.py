@@ -1,13 +1,20 @@
-"""Drop-in for the inference glue of /root/reference/evaluate/coco_eval.py: `get_outputs` (:80-114) and
-`handle_paf_and_heat` (:197-242).  COCO mAP scoring (eval_coco / run_eval with pycocotools) is outside the hot
-path and not provided.  Unlike the reference this module does not parse sys.argv at import;
-`cfg` is the shared lib.config node."""
+"""Drop-in for /root/reference/evaluate/coco_eval.py: the inference glue `get_outputs` (:80-114) and
+`handle_paf_and_heat` (:197-242), and the evaluation loop around it: `append_result` (:117-154),
+`eval_coco` (:56-76), `run_eval` (:245-283).  pycocotools is imported when the evaluation loop is used (it is absent
+from the build image); the network and the post-processing run on the GPU through libb200pose.so.
+Unlike the reference this module does not parse sys.argv at import; `cfg` is the shared lib.config node."""
+import json
+import os
+
+import cv2
 import numpy as np
 import torch
 
 from ..lib.config import cfg
 from ..lib.datasets.preprocessing import (inception_preprocess, rtpose_preprocess, ssd_preprocess, vgg_preprocess)
 from ..lib.network import im_transform
+from ..lib.utils.common import draw_humans
+from ..lib.utils.paf_to_pose import paf_to_pose_cpp
 
 ORDER_COCO = [0, 15, 14, 17, 16, 5, 2, 6, 3, 7, 4, 11, 8, 12, 9, 13, 10]   # coco_eval.py:52
 
@@ -44,3 +51,65 @@ def handle_paf_and_heat(normal_heat, flipped_heat, normal_paf, flipped_paf):
     averaged_paf = (normal_paf + mirrored[:, :, _SWAP_PAF]) / 2.
     averaged_heatmap = (normal_heat + flipped_heat[:, ::-1, :][:, :, _SWAP_HEAT]) / 2.
     return averaged_paf, averaged_heatmap
+
+
+def append_result(image_id, humans, upsample_keypoints, outputs):
+    """coco_eval.py:117-154: one COCO keypoint record per person.  `upsample_keypoints` = (height, width) of the
+    network input mapped back to the original image; the 18 parts are reordered to COCO's 17 (ORDER_COCO drops the
+    neck), visible parts get v = 1, the record score is the constant 1."""
+    for human in humans:
+        keypoints = np.zeros((18, 3))
+        for i in range(cfg.MODEL.NUM_KEYPOINTS):
+            part = human.body_parts.get(i)
+            if part is not None:
+                keypoints[i] = (part.x * upsample_keypoints[1] + 0.5, part.y * upsample_keypoints[0] + 0.5, 1)
+        outputs.append({"image_id": image_id, "category_id": 1, "keypoints": list(keypoints[ORDER_COCO, :].reshape(51)),
+                        "score": 1.})
+
+
+def _pycocotools():
+    try:
+        from pycocotools.coco import COCO
+        from pycocotools.cocoeval import COCOeval
+    except ImportError as e:       # loud: the reference imports it at module level
+        raise ImportError("run_eval / eval_coco need pycocotools (not installed in this image): %s" % e)
+    return COCO, COCOeval
+
+
+def eval_coco(outputs, annFile, imgIds):
+    """coco_eval.py:56-76: keypoint mAP of `outputs` with pycocotools (through a temporary results.json)."""
+    COCO, COCOeval = _pycocotools()
+    with open('results.json', 'w') as f:
+        json.dump(outputs, f)
+    coco_gt = COCO(annFile)
+    coco_dt = coco_gt.loadRes('results.json')
+    ev = COCOeval(coco_gt, coco_dt, 'keypoints')
+    ev.params.imgIds = imgIds
+    ev.evaluate()
+    ev.accumulate()
+    ev.summarize()
+    os.remove('results.json')
+    return ev.stats[0]
+
+
+def run_eval(image_dir, anno_file, vis_dir, model, preprocess):
+    """coco_eval.py:245-283: every person image of the annotation file -> get_outputs -> paf_to_pose_cpp ->
+    visualisation written to vis_dir -> COCO records -> mAP."""
+    COCO, _ = _pycocotools()
+    coco = COCO(anno_file)
+    img_ids = coco.getImgIds(catIds=coco.getCatIds(catNms=['person']))
+    print("Total number of validation images {}".format(len(img_ids)))
+    outputs = []
+    print("Processing Images in validation set")
+    for i, img_id in enumerate(img_ids):
+        if i % 10 == 0 and i != 0:
+            print("Processed {} images".format(i))
+        file_name = coco.loadImgs(img_id)[0]['file_name']
+        ori = cv2.imread(os.path.join(image_dir, file_name))
+        paf, heatmap, scale_img = get_outputs(ori, model, preprocess)
+        humans = paf_to_pose_cpp(heatmap, paf, cfg)
+        cv2.imwrite(os.path.join(vis_dir, file_name), draw_humans(ori, humans))
+        upsample_keypoints = (heatmap.shape[0] * cfg.MODEL.DOWNSAMPLE / scale_img,
+                              heatmap.shape[1] * cfg.MODEL.DOWNSAMPLE / scale_img)
+        append_result(img_id, humans, upsample_keypoints, outputs)
+    return eval_coco(outputs=outputs, annFile=anno_file, imgIds=img_ids)

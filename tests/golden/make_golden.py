@@ -14,7 +14,7 @@ import os
 import sys
 import types
 
-ARGS = sys.argv[1:]     # optional: "crop" regenerates only the crop_with_factor fixture
+ARGS = sys.argv[1:]     # optional: "crop" / "eval" regenerate only those small fixtures
 
 import numpy as np
 
@@ -103,13 +103,44 @@ def make_crop():
     np.savez_compressed(os.path.join(OUT, "crop_with_factor.npz"), **out)
 
 
+def eval_humans(Human, BodyPart, seed=17, count=5):
+    """Seeded synthetic persons (some parts missing) for the append_result fixture; the same generator is used by the
+    test with the product's Human / BodyPart classes."""
+    rs = np.random.RandomState(seed)
+    humans = []
+    for k in range(count):
+        hm = Human([])
+        for p in range(18):
+            if rs.rand() < 0.75:
+                hm.body_parts[p] = BodyPart('%d-%d' % (k, p), p, float(rs.rand()), float(rs.rand()), float(rs.rand()))
+        hm.score = float(rs.rand())
+        humans.append(hm)
+    return humans
+
+
+def make_eval(ref_eval):
+    """append_result (evaluate/coco_eval.py:117-154) of the reference on seeded persons."""
+    from lib.utils.common import BodyPart, Human
+    outputs = []
+    ref_eval.append_result(42, eval_humans(Human, BodyPart), (368 / 0.71, 496 / 0.71), outputs)
+    np.savez_compressed(os.path.join(OUT, "append_result.npz"),
+                        keypoints=np.array([o["keypoints"] for o in outputs], np.float64),
+                        score=np.array([o["score"] for o in outputs], np.float64),
+                        image_id=np.array([o["image_id"] for o in outputs]),
+                        category_id=np.array([o["category_id"] for o in outputs]),
+                        keys=np.array(list(outputs[0].keys())))
+    print("append_result", len(outputs), "records")
+
+
 def main():
     import torch
     get_model, ref_p2p, ref_eval, cfg = import_reference()
     if not ARGS or "crop" in ARGS:
         make_crop()
-        if ARGS == ["crop"]:
-            return
+    if not ARGS or "eval" in ARGS:
+        make_eval(ref_eval)
+    if ARGS and set(ARGS) <= {"crop", "eval"}:
+        return
     torch.manual_seed(0)
 
     # ---------------- network (rtpose_model.forward) ----------------

@@ -243,6 +243,82 @@ def test_crop_geometry_and_python_wrappers_without_a_gpu(built, monkeypatch):
         pe.infer_images([np.zeros((4, 4), np.uint8)])
 
 
+def _eval_humans(Human, BodyPart, seed=17, count=5):
+    """Same generator as tests/golden/make_golden.py::eval_humans (which fed the reference's append_result)."""
+    rs = np.random.RandomState(seed)
+    humans = []
+    for k in range(count):
+        hm = Human([])
+        for p in range(18):
+            if rs.rand() < 0.75:
+                hm.body_parts[p] = BodyPart('%d-%d' % (k, p), p, float(rs.rand()), float(rs.rand()), float(rs.rand()))
+        hm.score = float(rs.rand())
+        humans.append(hm)
+    return humans
+
+
+def test_append_result_matches_reference_golden():
+    """COCO record formatting (coco_eval.py:117-154): 18 -> 17 keypoint reorder, un-scaling, constant score."""
+    ev = pkg_module("evaluate.coco_eval")
+    common = pkg_module("lib.utils.common")
+    f = golden("append_result")
+    outputs = []
+    ev.append_result(42, _eval_humans(common.Human, common.BodyPart), (368 / 0.71, 496 / 0.71), outputs)
+    assert len(outputs) == len(f["keypoints"]) == 5
+    for o, kp, sc, iid, cid in zip(outputs, f["keypoints"], f["score"], f["image_id"], f["category_id"]):
+        assert list(o.keys()) == list(f["keys"]) and len(o["keypoints"]) == 51
+        np.testing.assert_array_equal(np.array(o["keypoints"], np.float64), kp)
+        assert o["score"] == sc and o["image_id"] == iid and o["category_id"] == cid
+
+
+def test_run_eval_plumbing_with_stub_pycocotools(monkeypatch, tmp_path):
+    """run_eval (coco_eval.py:245-283) end to end on the host side: image listing, visualisation files, COCO records,
+    results.json round trip - with get_outputs / paf_to_pose_cpp (the GPU calls) and pycocotools stubbed."""
+    import json
+    import types
+    import cv2
+    ev = pkg_module("evaluate.coco_eval")
+    common = pkg_module("lib.utils.common")
+    img_dir, vis_dir = tmp_path / "img", tmp_path / "vis"
+    img_dir.mkdir(); vis_dir.mkdir()
+    rs = np.random.RandomState(2)
+    for name, shape in (("a.jpg", (60, 80, 3)), ("b.jpg", (90, 70, 3))):
+        cv2.imwrite(str(img_dir / name), rs.randint(0, 256, shape).astype(np.uint8))
+    seen = {}
+
+    class COCO:
+        def __init__(self, anno): seen["anno"] = anno
+        def getCatIds(self, catNms): return [1]
+        def getImgIds(self, catIds): return [7, 9]
+        def loadImgs(self, i): return [{"file_name": {7: "a.jpg", 9: "b.jpg"}[i]}]
+        def loadRes(self, path): seen["results"] = json.load(open(path)); return "dt"
+
+    class COCOeval:
+        def __init__(self, gt, dt, kind): self.params = types.SimpleNamespace(imgIds=None); self.stats = [0.5]; seen["kind"] = kind
+        def evaluate(self): seen["imgIds"] = self.params.imgIds
+        def accumulate(self): pass
+        def summarize(self): pass
+    for name, attrs in (("pycocotools", {}), ("pycocotools.coco", {"COCO": COCO}), ("pycocotools.cocoeval", {"COCOeval": COCOeval})):
+        m = types.ModuleType(name); m.__dict__.update(attrs); monkeypatch.setitem(sys.modules, name, m)
+    humans = _eval_humans(common.Human, common.BodyPart, seed=3, count=2)
+    monkeypatch.setattr(ev, "get_outputs", lambda img, model, pre: (np.zeros((46, 62, 38), np.float32),
+                                                                    np.zeros((46, 62, 19), np.float32), 368.0 / min(img.shape[:2])))
+    monkeypatch.setattr(ev, "paf_to_pose_cpp", lambda heat, paf, cfg: humans)
+    monkeypatch.chdir(tmp_path)
+    assert ev.run_eval(str(img_dir), "anno.json", str(vis_dir), model=None, preprocess="rtpose") == 0.5
+    assert sorted(os.listdir(vis_dir)) == ["a.jpg", "b.jpg"] and not os.path.exists(tmp_path / "results.json")
+    assert seen["kind"] == "keypoints" and seen["imgIds"] == [7, 9] and len(seen["results"]) == 4
+    want = []
+    ev.append_result(7, humans, (46 * 8 / (368.0 / 60), 62 * 8 / (368.0 / 60)), want)
+    assert seen["results"][:2] == json.loads(json.dumps(want))
+    # the import-compatibility surface of evaluate/evaluation.py:4-7
+    from evaluate.coco_eval import run_eval                                   # noqa: F401
+    from lib.network.openpose import OpenPose_Model, use_vgg                  # noqa: F401
+    from lib.network.rtpose_vgg import get_model, use_vgg as use_vgg2         # noqa: F401
+    with pytest.raises(NotImplementedError):
+        OpenPose_Model(l2_stages=4, l1_stages=2, paf_out_channels=38, heat_out_channels=19)
+
+
 @pytest.mark.parametrize("name", sorted(POST_CASES))
 def test_device_cores_on_host_match_oracle(name, built):
     """csrc/post_core.h (pair scoring, std::sort emulation, greedy matching, indexed person assembly) compiled
