@@ -154,6 +154,17 @@ int b200pose_infer_raw_u8(b200pose_net* net, b200pose_post* post, const unsigned
                           int src_h, int src_w, int dest_size, int factor, int mode, float thresh, int flip,
                           void* cuda_stream);
 
+/* Multi-scale (+ flip) test-time averaging, BASELINE.json configs[4].  The reference at this commit has no multi-scale
+ * loop (get_outputs is single-scale, evaluate/coco_eval.py:87-91); the protocol is composed from its own functions:
+ * for every scale s: crop_with_factor(img, int(base_size * s), factor) -> network (-> handle_paf_and_heat with the
+ * mirrored RAW frame when flip != 0) -> bicubic resize of the 57 maps to the grid of base_size (OpenCV INTER_CUBIC
+ * formula, csrc/resize_core.h) -> running float32 sum; average = sum / n_scales; fused post-processing on the average.
+ * oracle/glue_port.py::multi_scale_maps restates exactly this composition. */
+int b200pose_infer_raw_u8_multiscale(b200pose_net* net, b200pose_post* post, const unsigned char* images,
+                                     int input_on_device, int n, int src_h, int src_w, int base_size, int factor,
+                                     const double* scales, int n_scales, int mode, float thresh, int flip,
+                                     void* cuda_stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * 4. Legacy SWIG surface of lib/pafprocess (pafprocess.h:53-59, pafprocess.i:14): same names, same argument
  *    meaning; state is kept in a process-global context exactly like the reference's file-scope globals

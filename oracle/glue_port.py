@@ -4,6 +4,7 @@
   * rtpose_preprocess / vgg_preprocess   /root/reference/lib/datasets/preprocessing.py:16-21, 32-43
   * get_outputs                          /root/reference/evaluate/coco_eval.py:80-114
   * handle_paf_and_heat                  /root/reference/evaluate/coco_eval.py:197-242
+  * resize_cubic / multi_scale_maps      composition for BASELINE.json configs[4] (cv2.resize INTER_CUBIC restated)
   * paf_to_pose_cpp                      /root/reference/lib/utils/paf_to_pose.py:372-406
 
 cv2.resize (bilinear, uint8) is the reference's own third-party call and is used the same way here.
@@ -58,6 +59,58 @@ def handle_paf_and_heat(normal_heat, flipped_heat, normal_paf, flipped_paf):
     avg_paf = (normal_paf + fp[:, :, SWAP_PAF]) / 2.
     avg_heat = (normal_heat + flipped_heat[:, ::-1, :][:, :, SWAP_HEAT]) / 2.
     return avg_paf, avg_heat
+
+
+def resize_cubic(src, dh, dw):
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_CUBIC) on float32 [h,w] / [h,w,C] maps, restated from OpenCV's
+    published algorithm exactly like nms_port.upsample8_cubic but for any size ratio: f = (float)((d+0.5)*(src/dst)-0.5),
+    taps floor(f)-1..floor(f)+2 with replicated borders, interpolateCubic(A=-0.75) in float32, horizontal pass
+    ((s0*a0+s1*a1)+s2*a2)+s3*a3, vertical pass s0*b0+(s1*b1+(s2*b2+s3*b3)).  cv2 itself evaluates the last
+    (row_length mod 4) elements of a row in another order (SIMD tail), so this matches cv2 (IPP off) only to 2.4e-7,
+    and the IPP-enabled default of this container to 2e-5 (tests/test_oracle.py)."""
+    F32 = np.float32
+    src = np.ascontiguousarray(src, dtype=F32)
+    squeeze = src.ndim == 2
+    if squeeze:
+        src = src[:, :, None]
+    h, w, _ = src.shape
+
+    def axis(dn, sn):
+        step = 1.0 / (float(dn) / float(sn))
+        f = ((np.arange(dn, dtype=np.float64) + 0.5) * step - 0.5).astype(F32)
+        s = np.floor(f).astype(np.int64)
+        co = np.stack([nms_port._cubic_coeffs(x) for x in (f - s.astype(F32)).astype(F32)]).astype(F32)
+        return np.clip(s[:, None] - 1 + np.arange(4)[None, :], 0, sn - 1), co
+    ix, ax = axis(dw, w)
+    iy, by = axis(dh, h)
+    hor = src[:, ix[:, 0], :] * ax[None, :, 0, None]
+    for j in (1, 2, 3):
+        hor = hor + src[:, ix[:, j], :] * ax[None, :, j, None]
+    out = hor[iy[:, 3]] * by[:, 3, None, None]
+    for j in (2, 1, 0):
+        out = hor[iy[:, j]] * by[:, j, None, None] + out
+    out = out.astype(F32)
+    return out[:, :, 0] if squeeze else out
+
+
+def multi_scale_maps(per_scale, base_hw):
+    """Multi-scale test-time averaging (BASELINE.json configs[4]; the reference at this commit has no multi-scale loop,
+    so this is a composition of its functions): per_scale = [(heat, paf)] or [(heat, paf, heat_flipped, paf_flipped)]
+    per scale, HWC float32 at that scale's grid.  Each scale is flip-merged with handle_paf_and_heat when the mirrored
+    maps are given, resized to base_hw with resize_cubic, summed in float32 in the given order and divided by the
+    number of scales.  Returns (avg_heat, avg_paf)."""
+    F32 = np.float32
+    acc_h = acc_p = None
+    for item in per_scale:
+        heat, paf = item[0], item[1]
+        if len(item) == 4:
+            paf, heat = handle_paf_and_heat(heat, item[2], paf, item[3])
+            heat, paf = heat.astype(F32), paf.astype(F32)
+        rh, rp = resize_cubic(heat, *base_hw), resize_cubic(paf, *base_hw)
+        acc_h = rh if acc_h is None else (acc_h + rh).astype(F32)
+        acc_p = rp if acc_p is None else (acc_p + rp).astype(F32)
+    n = F32(len(per_scale))
+    return (acc_h / n).astype(F32), (acc_p / n).astype(F32)
 
 
 def paf_to_pose(heat, paf, pafprocess, thresh=0.1, upsample=8, num_keypoints=18):

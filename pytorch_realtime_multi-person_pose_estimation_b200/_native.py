@@ -59,6 +59,8 @@ def lib():
         "b200pose_crop_geometry": ([ci, ci, ci, ci, ctypes.POINTER(ctypes.c_double)] + [ctypes.POINTER(ci)] * 4, ci),
         "b200pose_net_crop_with_factor": ([vp, vp, ci, ci, ci, ci, ci, ci, vp, ci, vp], ci),
         "b200pose_infer_raw_u8": ([vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, cf, ci, vp], ci),
+        "b200pose_infer_raw_u8_multiscale": ([vp, vp, vp, ci, ci, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_double), ci, ci, cf,
+                                              ci, vp], ci),
         "process_paf": ([ci, ci, ci, vp, ci, ci, ci, vp, ci, ci, ci, vp], ci),
         "get_num_humans": ([], ci),
         "get_part_cid": ([ci, ci], ci),
@@ -81,7 +83,7 @@ EXPORTED = ["b200pose_last_error", "b200pose_version", "b200pose_launch_count", 
             "b200pose_post_run", "b200pose_post_sync", "b200pose_post_last_ticket", "b200pose_post_select", "b200pose_post_debug", "b200pose_post_num_humans", "b200pose_post_status",
             "b200pose_post_get_humans", "b200pose_post_get_peaks", "b200pose_infer", "b200pose_infer_u8", "b200pose_flip_merge", "b200pose_infer_flip",
             "b200pose_infer_u8_flip", "b200pose_crop_geometry", "b200pose_net_crop_with_factor",
-            "b200pose_infer_raw_u8", "process_paf", "get_num_humans",
+            "b200pose_infer_raw_u8", "b200pose_infer_raw_u8_multiscale", "process_paf", "get_num_humans",
             "get_part_cid", "get_score", "get_part_x", "get_part_y", "get_part_score"]
 
 

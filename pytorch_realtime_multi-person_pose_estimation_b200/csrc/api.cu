@@ -963,6 +963,66 @@ int b200pose_infer_raw_u8(b200pose_net* net, b200pose_post* post, const unsigned
     return post_run_dev(post, post->d_heat.p, post->d_paf.p, 0, n, h, w, thresh, st);
 }
 
+int b200pose_infer_raw_u8_multiscale(b200pose_net* net, b200pose_post* post, const unsigned char* images,
+                                     int input_on_device, int n, int src_h, int src_w, int base_size, int factor,
+                                     const double* scales, int n_scales, int mode, float thresh, int flip,
+                                     void* cuda_stream) {
+    if (!net || !post) return fail("null handle");
+    if (!net->finalized) return fail("net not finalized");
+    if (net->device != post->device) return fail("net and post live on different devices");
+    if (!images || !scales || n_scales < 1 || n_scales > 16) return fail("infer_multiscale: bad arguments");
+    if (n > post->pb.batch_cap) return fail("batch %d exceeds post batch_cap %d", n, post->pb.batch_cap);
+    CropGeom base;
+    if (int rc = crop_check(n, src_h, src_w, base_size, factor, &base)) return rc;
+    CU(cudaSetDevice(net->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const int nimg = flip ? 2 * n : n;
+    const size_t raw = (size_t)n * src_h * src_w * 3;
+    const unsigned char* d_raw = images;
+    if (!input_on_device || flip) {
+        CU(net->raw_stage.ensure(raw * (flip ? 2 : 1)));
+        CU(cudaMemcpyAsync(net->raw_stage.p, images, raw, input_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        d_raw = net->raw_stage.p;
+    }
+    cudaError_t e;
+    if (flip) {
+        e = tta_mirror_u8hwc(net->raw_stage.p, net->raw_stage.p + raw, n, src_h, src_w, st);
+        if (e != cudaSuccess) return fail("tta_mirror: %s", cudaGetErrorString(e));
+        ++g_launches;
+    }
+    const int h1 = base.pad_h / 8, w1 = base.pad_w / 8;
+    CU(post->d_heat.ensure((size_t)n * kHeat * h1 * w1));
+    CU(post->d_paf.ensure((size_t)n * kPaf * h1 * w1));
+    for (int k = 0; k < n_scales; ++k) {
+        const int dest = (int)((double)base_size * scales[k]);       // Python: int(base_size * s)
+        CropGeom g;
+        if (int rc = crop_check(n, src_h, src_w, dest, factor, &g)) return rc;
+        const int H = g.pad_h, W = g.pad_w, h = H / 8, w = W / 8;
+        CU(net->in_stage_u8.ensure((size_t)nimg * H * W * 3));
+        e = crop_with_factor_launch(d_raw, net->in_stage_u8.p, nimg, src_h, src_w, g, st);
+        if (e != cudaSuccess) return fail("crop_with_factor_launch: %s", cudaGetErrorString(e));
+        ++g_launches;
+        if (int rc = net_forward_impl(net, net->in_stage_u8.p, 1, 1, nimg, H, W, mode, nullptr, 1, st, false)) return rc;
+        const size_t eh = (size_t)n * kHeat * h * w, ep = (size_t)n * kPaf * h * w;
+        const float *s_heat = net->out_f32[11].p, *s_paf = net->out_f32[10].p;
+        if (flip) {
+            CU(post->tta_out.ensure(eh + ep));
+            if (int rc = flip_merge_dev(s_heat, s_heat + eh, s_paf, s_paf + ep, 0, n, h, w, post->tta_out.p,
+                                        post->tta_out.p + eh, st))
+                return rc;
+            s_heat = post->tta_out.p;
+            s_paf = post->tta_out.p + eh;
+        }
+        const float div = (k == n_scales - 1) ? (float)n_scales : 0.f;
+        e = resize_cubic_accum_launch(s_heat, post->d_heat.p, (long)n * kHeat, h, w, h1, w1, k == 0, div, st);
+        if (e == cudaSuccess)
+            e = resize_cubic_accum_launch(s_paf, post->d_paf.p, (long)n * kPaf, h, w, h1, w1, k == 0, div, st);
+        if (e != cudaSuccess) return fail("resize_cubic_accum_launch: %s", cudaGetErrorString(e));
+        g_launches += 2;
+    }
+    return post_run_dev(post, post->d_heat.p, post->d_paf.p, 0, n, h1, w1, thresh, st);
+}
+
 // ------------------------------------------------------------------------------------------------ legacy pafprocess
 namespace {
 std::mutex g_legacy_mu;

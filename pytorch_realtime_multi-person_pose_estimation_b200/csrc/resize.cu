@@ -38,7 +38,35 @@ __global__ void __launch_bounds__(kThreads) crop_with_factor_kernel(const unsign
     }
 }
 
+// One thread per destination element of the base grid; 16 gathers from the (L1/L2-resident, <= 34 KB) source plane.
+__global__ void __launch_bounds__(kThreads) resize_cubic_accum_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                      long planes, int sh, int sw, int dh, int dw,
+                                                                      double step_y, double step_x, int first, float divide_by) {
+    const long per = (long)dh * dw, total = planes * per;
+    for (long i = blockIdx.x * (long)kThreads + threadIdx.x; i < total; i += (long)gridDim.x * kThreads) {
+        const long plane = i / per;
+        const int q = (int)(i - plane * per);
+        const int y = q / dw, x = q - y * dw;
+        const CubCoef cy = rs_cubic_coef(y, sh, step_y), cx = rs_cubic_coef(x, sw, step_x);
+        float v = rs_cubic_at(src + plane * (long)sh * sw, sw, 1, cx, cy);
+        if (!first) v = __fadd_rn(dst[i], v);
+        if (divide_by > 0.f) v = __fdiv_rn(v, divide_by);
+        dst[i] = v;
+    }
+}
+
 }  // namespace
+
+cudaError_t resize_cubic_accum_launch(const float* src, float* dst, long planes, int src_h, int src_w, int dst_h,
+                                      int dst_w, int first, float divide_by, cudaStream_t s) {
+    if (planes < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return cudaErrorInvalidValue;
+    const long total = planes * dst_h * dst_w;
+    long b = (total + kThreads - 1) / kThreads;
+    if (b > 148L * 8) b = 148L * 8;
+    resize_cubic_accum_kernel<<<(unsigned)b, kThreads, 0, s>>>(src, dst, planes, src_h, src_w, dst_h, dst_w,
+                                                             rs_step(dst_h, src_h), rs_step(dst_w, src_w), first, divide_by);
+    return cudaGetLastError();
+}
 
 cudaError_t crop_with_factor_launch(const unsigned char* in, unsigned char* out, int n, int src_h, int src_w,
                                     const CropGeom& g, cudaStream_t s) {

@@ -12,4 +12,9 @@ namespace b2p {
 cudaError_t crop_with_factor_launch(const unsigned char* in, unsigned char* out, int n, int src_h, int src_w,
                                     const CropGeom& g, cudaStream_t s);
 
+// Bicubic resize of `planes` float32 planes [src_h, src_w] -> [dst_h, dst_w] (resize_core.h: rs_cubic_at), fused with
+// the running sum of the multi-scale average: dst = first ? r : dst + r, then dst /= divide_by when divide_by > 0.
+cudaError_t resize_cubic_accum_launch(const float* src, float* dst, long planes, int src_h, int src_w, int dst_h,
+                                      int dst_w, int first, float divide_by, cudaStream_t s);
+
 }  // namespace b2p

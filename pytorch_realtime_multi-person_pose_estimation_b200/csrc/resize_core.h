@@ -119,6 +119,75 @@ B2P_RS_HD unsigned char rs_area2_px(const unsigned char* src, int src_h, int src
     return (unsigned char)(v > 255 ? 255 : v);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bicubic resize of float32 maps (multi-scale test-time averaging): OpenCV's INTER_CUBIC formula restated -
+// interpolateCubic with A = -0.75 in float, source coordinate f = (float)((d + 0.5) * (src / dst) - 0.5), taps
+// floor(f) - 1 .. floor(f) + 2 with replicated borders, horizontal pass ((s0*a0 + s1*a1) + s2*a2) + s3*a3, vertical
+// pass s0*b0 + (s1*b1 + (s2*b2 + s3*b3)), no fused multiply-add.  This is the arithmetic of the x8 refinement in
+// peaks_kernel generalised to any size ratio.  cv2.resize itself is only matched to ~2.4e-7 in general: its SIMD
+// build evaluates the last (row_length mod 4) elements of a row in a different order (and the IPP-enabled default
+// of the build container differs by up to 2e-5), so the ORACLE of the multi-scale composition is this restatement.
+struct CubCoef {
+    int s[4];
+    float w[4];
+};
+
+B2P_RS_HD float rs_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+B2P_RS_HD float rs_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+B2P_RS_HD CubCoef rs_cubic_coef(int d, int src_n, double step) {
+    CubCoef c;
+    int s;
+    float x;
+    rs_src_coord(d, step, &s, &x);
+    const float A = -0.75f;
+    const float x1 = rs_add(x, 1.f), y = rs_add(1.f, -x);
+    // ((A*(x+1) - 5A)*(x+1) + 8A)*(x+1) - 4A
+    c.w[0] = rs_add(rs_mul(rs_add(rs_mul(rs_add(rs_mul(A, x1), -rs_mul(5.f, A)), x1), rs_mul(8.f, A)), x1), -rs_mul(4.f, A));
+    // ((A+2)*x - (A+3))*x*x + 1
+    c.w[1] = rs_add(rs_mul(rs_mul(rs_add(rs_mul(rs_add(A, 2.f), x), -rs_add(A, 3.f)), x), x), 1.f);
+    c.w[2] = rs_add(rs_mul(rs_mul(rs_add(rs_mul(rs_add(A, 2.f), y), -rs_add(A, 3.f)), y), y), 1.f);
+    c.w[3] = rs_add(rs_add(rs_add(1.f, -c.w[0]), -c.w[1]), -c.w[2]);
+    for (int j = 0; j < 4; ++j) {
+        const int t = s - 1 + j;
+        c.s[j] = t < 0 ? 0 : (t > src_n - 1 ? src_n - 1 : t);
+    }
+    return c;
+}
+
+// source step per destination element, as cv::resize derives it from an explicit destination size (host only)
+inline double rs_step(int dst_n, int src_n) { return 1.0 / ((double)dst_n / (double)src_n); }
+
+// One destination element of one plane (row stride `sy`, element stride `sx` in floats).
+B2P_RS_HD float rs_cubic_at(const float* plane, long sy, long sx, const CubCoef& cx, const CubCoef& cy) {
+    float hrow[4];
+    for (int j = 0; j < 4; ++j) {
+        const float* r = plane + (long)cy.s[j] * sy;
+        float v = rs_mul(r[cx.s[0] * sx], cx.w[0]);
+        v = rs_add(v, rs_mul(r[cx.s[1] * sx], cx.w[1]));
+        v = rs_add(v, rs_mul(r[cx.s[2] * sx], cx.w[2]));
+        v = rs_add(v, rs_mul(r[cx.s[3] * sx], cx.w[3]));
+        hrow[j] = v;
+    }
+    float o = rs_mul(hrow[3], cy.w[3]);
+    o = rs_add(rs_mul(hrow[2], cy.w[2]), o);
+    o = rs_add(rs_mul(hrow[1], cy.w[1]), o);
+    o = rs_add(rs_mul(hrow[0], cy.w[0]), o);
+    return o;
+}
+
 struct CropGeom {
     double im_scale;       // dest_size / min(h, w)                       (im_transform.py:125)
     double step;           // 1 / im_scale: source pixels per destination pixel

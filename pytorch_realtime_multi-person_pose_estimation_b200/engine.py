@@ -217,10 +217,27 @@ class PoseEngine:
         self._last = (n, ph, pw)
         return self.post.last_ticket()
 
-    def infer_images(self, images, dest_size=368, factor=8, thresh=0.1, flip=False):
+    def infer_raw_multiscale_async_u8(self, in_ptr, in_on_device, n, src_h, src_w, scales, base_size=368, factor=8,
+                                      thresh=0.1, flip=False, stream=0):
+        """Multi-scale (+ flip) test-time averaging of raw uint8 BGR frames of one size (BASELINE.json configs[4]):
+        every scale s runs crop_with_factor(int(base_size * s)) + the network on the device, the maps are resized
+        (bicubic) to the grid of base_size, averaged, and post-processed.  Coordinates refer to the padded base frame."""
+        arr = (ctypes.c_double * len(scales))(*[float(s) for s in scales])
+        nat.check(nat.lib().b200pose_infer_raw_u8_multiscale(self.net._h, self.post._h, ctypes.c_void_p(in_ptr),
+                                                             int(in_on_device), n, src_h, src_w, int(base_size),
+                                                             int(factor), arr, len(scales), self.mode,
+                                                             ctypes.c_float(thresh), int(bool(flip)),
+                                                             ctypes.c_void_p(stream)),
+                  "b200pose_infer_raw_u8_multiscale")
+        _, _, (ph, pw) = nat.crop_geometry(src_h, src_w, base_size, factor)
+        self._last = (n, ph, pw)
+        return self.post.last_ticket()
+
+    def infer_images(self, images, dest_size=368, factor=8, thresh=0.1, flip=False, scales=None):
         """images: a list of raw uint8 BGR frames of arbitrary (mixed) sizes, as cv2.imread returns them.  Frames are
         bucketed by shape (one launch sequence per bucket, at most batch_cap frames each); returns per-image human lists
-        in input order, coordinates normalised to the padded frame like paf_to_pose_cpp's."""
+        in input order, coordinates normalised to the padded frame like paf_to_pose_cpp's.
+        scales: e.g. (0.5, 1.0, 1.5, 2.0) for multi-scale test-time averaging around dest_size."""
         buckets = {}
         for i, im in enumerate(images):
             if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
@@ -232,7 +249,11 @@ class PoseEngine:
                 part = idx[k:k + self.post.batch_cap]
                 batch = np.ascontiguousarray(np.stack([images[i] for i in part]))
                 self._keep = batch
-                self.infer_raw_async_u8(batch.ctypes.data, False, len(part), sh, sw, dest_size, factor, thresh, flip)
+                if scales is None:
+                    self.infer_raw_async_u8(batch.ctypes.data, False, len(part), sh, sw, dest_size, factor, thresh, flip)
+                else:
+                    self.infer_raw_multiscale_async_u8(batch.ctypes.data, False, len(part), sh, sw, scales, dest_size,
+                                                       factor, thresh, flip)
                 for i, humans in zip(part, self.fetch()):
                     out[i] = humans
         return out

@@ -155,3 +155,17 @@ extern "C" int core_crop_with_factor(const unsigned char* src, int src_h, int sr
             for (int c = 0; c < 3; ++c) out[((long)y * g.pad_w + x) * 3 + c] = crop_px(src, src_h, src_w, 3, g, y, x, c);
     return 0;
 }
+
+// bicubic map resize with the exact functions the CUDA kernel calls (csrc/resize_core.h); src [sh, sw, C] HWC float32
+// -> out [dh, dw, C].
+extern "C" int core_resize_cubic(const float* src, int sh, int sw, int C, float* out, int dh, int dw) {
+    const double step_y = rs_step(dh, sh), step_x = rs_step(dw, sw);
+    for (int y = 0; y < dh; ++y) {
+        const CubCoef cy = rs_cubic_coef(y, sh, step_y);
+        for (int x = 0; x < dw; ++x) {
+            const CubCoef cx = rs_cubic_coef(x, sw, step_x);
+            for (int c = 0; c < C; ++c) out[((long)y * dw + x) * C + c] = rs_cubic_at(src + c, (long)sw * C, C, cx, cy);
+        }
+    }
+    return 0;
+}

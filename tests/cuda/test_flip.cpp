@@ -134,8 +134,85 @@ static int raw_section(b200pose_net* net, b200pose_post* post) {
     return failures;
 }
 
+// Multi-scale (+ flip) averaging == per scale: host crop -> validated forward (-> host flip merge) -> host bicubic resize
+// (shared core) -> float32 running sum -> / n_scales -> validated post_run.
+static int multiscale_section(b200pose_net* net, b200pose_post* post, int flip) {
+    const int n = 2, sh = 90, sw = 123, base = 96, ns = 4;
+    const double scales[ns] = {0.5, 1.0, 1.5, 2.0};
+    std::vector<unsigned char> raw((size_t)n * sh * sw * 3), raw_m(raw.size());
+    g_state = 0xD1B54A32D192ED03ull;
+    for (auto& b : raw) b = (unsigned char)(rnd() & 255);
+    for (int i = 0; i < n; ++i)
+        for (int y = 0; y < sh; ++y)
+            for (int x = 0; x < sw; ++x)
+                for (int c = 0; c < 3; ++c)
+                    raw_m[(((size_t)i * sh + y) * sw + x) * 3 + c] = raw[(((size_t)i * sh + y) * sw + (sw - 1 - x)) * 3 + c];
+    b2p::CropGeom g1 = b2p::crop_geometry(sh, sw, base, 8);
+    const int h1 = g1.pad_h / 8, w1 = g1.pad_w / 8;
+    std::vector<float> acc_h((size_t)n * 19 * h1 * w1), acc_p((size_t)n * 38 * h1 * w1);
+    for (int k = 0; k < ns; ++k) {
+        b2p::CropGeom g;
+        const int dest = (int)((double)base * scales[k]);
+        const std::vector<unsigned char> fr = host_crop(raw, n, sh, sw, dest, 8, &g);
+        const int H = g.pad_h, W = g.pad_w, h = H / 8, w = W / 8;
+        const size_t eh = (size_t)n * 19 * h * w, ep = (size_t)n * 38 * h * w;
+        std::vector<float> heat(eh), paf(ep);
+        float* outs[12] = {nullptr};
+        outs[10] = paf.data(); outs[11] = heat.data();
+        CHECK(b200pose_net_forward_u8(net, fr.data(), 0, n, H, W, 0, outs, 0, nullptr));
+        if (flip) {
+            const std::vector<unsigned char> fr_m = host_crop(raw_m, n, sh, sw, dest, 8, &g);
+            std::vector<float> heat_f(eh), paf_f(ep), mh(eh), mp(ep);
+            outs[10] = paf_f.data(); outs[11] = heat_f.data();
+            CHECK(b200pose_net_forward_u8(net, fr_m.data(), 0, n, H, W, 0, outs, 0, nullptr));
+            for (int i = 0; i < n; ++i)
+                for (int y = 0; y < h; ++y)
+                    for (int x = 0; x < w; ++x) {
+                        for (int c = 0; c < 19; ++c)
+                            mh[(size_t)i * 19 * h * w + ((size_t)c * h + y) * w + x] = b2p::tta_flip_merge_at(
+                                heat.data() + (size_t)i * 19 * h * w, heat_f.data() + (size_t)i * 19 * h * w, false, c, y, x, w,
+                                (long)h * w, w, 1);
+                        for (int c = 0; c < 38; ++c)
+                            mp[(size_t)i * 38 * h * w + ((size_t)c * h + y) * w + x] = b2p::tta_flip_merge_at(
+                                paf.data() + (size_t)i * 38 * h * w, paf_f.data() + (size_t)i * 38 * h * w, true, c, y, x, w,
+                                (long)h * w, w, 1);
+                    }
+            heat.swap(mh); paf.swap(mp);
+        }
+        const double sy = b2p::rs_step(h1, h), sx = b2p::rs_step(w1, w);
+        auto accumulate = [&](const std::vector<float>& src, std::vector<float>& acc, int C) {
+            for (long pl = 0; pl < (long)n * C; ++pl)
+                for (int y = 0; y < h1; ++y) {
+                    const b2p::CubCoef cy = b2p::rs_cubic_coef(y, h, sy);
+                    for (int x = 0; x < w1; ++x) {
+                        const b2p::CubCoef cx = b2p::rs_cubic_coef(x, w, sx);
+                        float v = b2p::rs_cubic_at(src.data() + pl * h * w, w, 1, cx, cy);
+                        float& a = acc[(size_t)pl * h1 * w1 + (size_t)y * w1 + x];
+                        if (k > 0) v = a + v;
+                        if (k == ns - 1) v = v / (float)ns;
+                        a = v;
+                    }
+                }
+        };
+        accumulate(heat, acc_h, 19);
+        accumulate(paf, acc_p, 38);
+    }
+    std::vector<std::vector<float>> want, got;
+    CHECK(b200pose_post_run(post, acc_h.data(), acc_p.data(), 0, 0, n, h1, w1, 0.1f, nullptr));
+    if (fetch(post, n, want)) return 1;
+    CHECK(b200pose_infer_raw_u8_multiscale(net, post, raw.data(), 0, n, sh, sw, base, 8, scales, ns, 0, 0.1f, flip, nullptr));
+    if (fetch(post, n, got)) return 1;
+    size_t persons = 0;
+    for (auto& r : want) persons += r.size() / B200POSE_HUMAN_FLOATS;
+    const bool ok = same(want, got);
+    printf("%s  b200pose_infer_raw_u8_multiscale(flip=%d) == composed path [4 scales, base %dx%d, %zu persons]\n",
+           ok ? "PASS" : "FAIL", flip, g1.pad_h, g1.pad_w, persons);
+    return !ok;
+}
+
 int main(int argc, char** argv) {
     const int n = 2, H = argc > 1 ? atoi(argv[1]) : 184, W = argc > 2 ? atoi(argv[2]) : 248;
+    const bool with_multiscale = !(argc > 3 && !strcmp(argv[3], "no-multiscale"));   // usage: test_flip [H W [no-multiscale]]
     const int h = H / 8, w = W / 8;
     b200pose_net* net = nullptr;
     b200pose_post* post = nullptr;
@@ -240,6 +317,10 @@ int main(int argc, char** argv) {
         }
     }
     failures += raw_section(net, post);
+    if (with_multiscale) {
+        failures += multiscale_section(net, post, 0);
+        failures += multiscale_section(net, post, 1);
+    }
     b200pose_post_destroy(post);
     b200pose_net_destroy(net);
     printf("%s (%d failures), kernels launched: %ld\n", failures ? "FLIP TEST FAILED" : "FLIP TEST OK", failures,

@@ -19,10 +19,21 @@ def test_flip_harness_through_the_c_abi(built):
     """tests/cuda/test_flip.cpp: fused b200pose_infer*_flip == forward x2 + host merge + post_run, bit for bit, in all
     three arithmetic modes; merge kernel == host core in both layouts; crop_with_factor kernel == host core;
     b200pose_infer_raw_u8 (with and without flip) == host crop + the uint8 entry points."""
-    r = subprocess.run([os.path.join(ROOT, "build", "test_flip"), "184", "248"], stdout=subprocess.PIPE,
+    r = subprocess.run([os.path.join(ROOT, "build", "test_flip"), "184", "248", "no-multiscale"], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=300)
     print(r.stdout)
     assert r.returncode == 0 and "FLIP TEST OK" in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.xfail(strict=False, reason="multi-scale averaging was written after round 1's GPU budget was spent; first "
+                   "hardware run of resize_cubic_accum_kernel is round 2")
+def test_multiscale_harness_through_the_c_abi(built):
+    """Same harness including the multi-scale sections: b200pose_infer_raw_u8_multiscale (flip 0 / 1) == per scale host
+    crop + validated forward + host merge + host bicubic resize (shared core) + float32 average + validated post_run."""
+    r = subprocess.run([os.path.join(ROOT, "build", "test_flip"), "184", "248"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0 and "FLIP TEST OK" in r.stdout and "multiscale(flip=1)" in r.stdout, r.stdout[-2000:]
 
 
 def test_flip_merge_kernel_matches_reference_golden(built):
@@ -118,6 +129,44 @@ def test_raw_frames_of_mixed_sizes_match_reference_shaped_pipeline(built, he_sd)
         heat = outs[11][0].permute(1, 2, 0).contiguous().cpu().numpy()
         paf = outs[10][0].permute(1, 2, 0).contiguous().cpu().numpy()
         _, want = glue_port.paf_to_pose(heat, paf, port)
+        assert_humans_equal(got[i], want, score_tol=0.0)
+        total += len(want)
+    assert total > 0
+
+
+@pytest.mark.xfail(strict=False, reason="multi-scale averaging was written after round 1's GPU budget was spent: its cores "
+                   "are verified on the host (tests/test_host.py), the first hardware run of the kernel is round 2")
+def test_multiscale_flip_averaging_matches_composed_oracle(built, he_sd):
+    """BASELINE.json configs[4] (multi-scale 0.5/1.0/1.5/2.0 with L/R flip): PoseEngine.infer_images(scales=..., flip=True)
+    == per scale the oracle's crop_with_factor of the frame and of the mirrored frame, the native uint8 forward, then the
+    oracle's handle_paf_and_heat, bicubic resize to the base grid, float32 average and paf_to_pose."""
+    eng = pkg_module("engine")
+    pe = eng.PoseEngine([v.numpy() for v in he_sd.values()], 0, mode="bf16", batch_cap=2, peak_cap=1024, human_cap=2048)
+    rs = np.random.RandomState(41)
+    imgs = [rs.randint(0, 256, (90, 123, 3)).astype(np.uint8) for _ in range(2)]
+    scales, base = (0.5, 1.0, 1.5, 2.0), 96
+    got = pe.infer_images(imgs, dest_size=base, factor=8, flip=True, scales=scales)
+    port = pafprocess_oracle.load_port()
+
+    def maps(frame, dest):
+        crop, _, _ = glue_port.crop_with_factor(frame, dest, 8)
+        H, W = crop.shape[:2]
+        outs = [torch.empty((1, 38 if k % 2 == 0 else 19, H // 8, W // 8), device="cuda") for k in range(12)]
+        xd = torch.from_numpy(np.ascontiguousarray(crop[None])).cuda()
+        pe.net.forward_u8_ptr(xd.data_ptr(), True, 1, H, W, pe.mode, [o.data_ptr() for o in outs], True,
+                              torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return (outs[11][0].permute(1, 2, 0).contiguous().cpu().numpy(), outs[10][0].permute(1, 2, 0).contiguous().cpu().numpy())
+    total = 0
+    for i, im in enumerate(imgs):
+        base_crop, _, _ = glue_port.crop_with_factor(im, base, 8)
+        per_scale = []
+        for s in scales:
+            heat, paf = maps(im, int(base * s))
+            heat_f, paf_f = maps(np.ascontiguousarray(im[:, ::-1]), int(base * s))
+            per_scale.append((heat, paf, heat_f, paf_f))
+        ah, ap = glue_port.multi_scale_maps(per_scale, (base_crop.shape[0] // 8, base_crop.shape[1] // 8))
+        _, want = glue_port.paf_to_pose(ah, ap, port)
         assert_humans_equal(got[i], want, score_tol=0.0)
         total += len(want)
     assert total > 0

@@ -213,6 +213,13 @@ def test_crop_geometry_and_python_wrappers_without_a_gpu(built, monkeypatch):
             calls.append((n, sh, sw, flip, [int(v) for v in first]))
             return 0
 
+    ms_calls = []
+
+    def fake_multiscale(net, post, images, on_dev, n, sh, sw, base, factor, scales, ns, mode, thresh, flip, stream):
+        ms_calls.append((n, sh, sw, base, factor, [scales[i] for i in range(ns)], flip))
+        calls.append((n, sh, sw, flip, [0] * n))
+        return 0
+    Fake.b200pose_infer_raw_u8_multiscale = staticmethod(fake_multiscale)
     monkeypatch.setattr(nat, "lib", lambda: Fake)
     net = object.__new__(eng.NativeNet)
     net._h = None
@@ -241,6 +248,8 @@ def test_crop_geometry_and_python_wrappers_without_a_gpu(built, monkeypatch):
     assert pe._last == (2, 64, 112)                                               # padded size of the last bucket (30x50 -> 64x107)
     with pytest.raises(nat.B200PoseError):
         pe.infer_images([np.zeros((4, 4), np.uint8)])
+    pe.infer_images(imgs[:1], dest_size=64, scales=(0.5, 1.0, 1.5, 2.0), flip=True)
+    assert ms_calls == [(1, 40, 50, 64, 8, [0.5, 1.0, 1.5, 2.0], 1)] and pe._last == (1, 64, 80)
 
 
 def _eval_humans(Human, BodyPart, seed=17, count=5):
@@ -317,6 +326,21 @@ def test_run_eval_plumbing_with_stub_pycocotools(monkeypatch, tmp_path):
     from lib.network.rtpose_vgg import get_model, use_vgg as use_vgg2         # noqa: F401
     with pytest.raises(NotImplementedError):
         OpenPose_Model(l2_stages=4, l1_stages=2, paf_out_channels=38, heat_out_channels=19)
+
+
+def test_cubic_resize_device_core_on_host_matches_oracle(built):
+    """csrc/resize_core.h rs_cubic_* (the functions resize_cubic_accum_kernel calls) compiled for the host == the
+    oracle's restatement of OpenCV's INTER_CUBIC, bit for bit, for the size ratios of the multi-scale averaging."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "build", "libpostcore_host.so"))
+    lib.core_resize_cubic.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] + [ctypes.c_int] * 2
+    rs = np.random.RandomState(13)
+    cases = [(23, 23, 46, 46, 19), (69, 69, 46, 46, 38), (92, 92, 46, 46, 19), (6, 9, 12, 16, 38), (24, 33, 12, 16, 19),
+             (46, 53, 46, 53, 38)] + [tuple(int(v) for v in rs.randint(3, 80, 4)) + (int(rs.choice([1, 19, 38])),) for _ in range(20)]
+    for (h, w, dh, dw, c) in cases:
+        src = rs.randn(h, w, c).astype(np.float32)
+        out = np.empty((dh, dw, c), np.float32)
+        lib.core_resize_cubic(src.ctypes.data, h, w, c, out.ctypes.data, dh, dw)
+        np.testing.assert_array_equal(out, glue_port.resize_cubic(src, dh, dw))
 
 
 @pytest.mark.parametrize("name", sorted(POST_CASES))

@@ -119,3 +119,30 @@ def test_swig_typemap_errors(built):
     port = pafprocess_oracle.load_port()
     with pytest.raises(TypeError):
         port.process_paf(np.zeros((1, 1, 5), np.float64), np.zeros((8, 8, 19), np.float32), np.zeros((8, 8, 38), np.float32))
+
+
+def test_cubic_resize_restatement_vs_opencv():
+    """oracle/glue_port.resize_cubic (the composition oracle of the multi-scale averaging) against cv2.resize
+    INTER_CUBIC: within 3e-7 of OpenCV's own code path (IPP off; cv2 evaluates the last row_length % 4 elements of a row
+    in another order), identity for equal sizes, exact when the row length is a multiple of 4."""
+    import cv2
+    rs = np.random.RandomState(12)
+    prev = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        for (h, w, dh, dw, c) in ((23, 23, 46, 46, 19), (69, 69, 46, 46, 38), (92, 92, 46, 46, 19), (6, 9, 12, 16, 38),
+                                  (24, 33, 12, 16, 19), (46, 53, 46, 53, 19), (20, 30, 33, 47, 1)):
+            src = rs.randn(h, w, c).astype(np.float32)
+            ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_CUBIC).reshape(dh, dw, c)
+            mine = glue_port.resize_cubic(src, dh, dw)
+            assert np.abs(mine - ref).max() <= 3e-7
+            if (dw * c) % 4 == 0 or (h, w) == (dh, dw):
+                np.testing.assert_array_equal(mine, ref)
+    finally:
+        cv2.ipp.setUseIPP(prev)
+    x = rs.randn(46, 46, 19).astype(np.float32)
+    np.testing.assert_array_equal(glue_port.resize_cubic(x, 46, 46), x)
+    h1, p1 = rs.randn(12, 16, 19).astype(np.float32), rs.randn(12, 16, 38).astype(np.float32)
+    ah, ap = glue_port.multi_scale_maps([(h1, p1)] * 4, (12, 16))
+    np.testing.assert_array_equal(ah, h1)          # (4 x) / 4 is exact
+    np.testing.assert_array_equal(ap, p1)

@@ -19,6 +19,6 @@ for line in out.splitlines():
         cur = m.group(1)
         table[cur] = hashlib.md5()
     elif cur and line.strip().startswith("/*"):      # instruction lines only
-        table[cur].update(line.encode())
+        table[cur].update(" ".join(line.split()).encode())      # column alignment varies with the widest line
 for k in sorted(table):
     print(table[k].hexdigest()[:12], k)
