@@ -3,6 +3,10 @@
  * Plain pointers and sizes only; no torch / numpy types.  Every entry point returns 0 on success and a
  * non-zero code on failure (b200pose_last_error() gives the text) unless stated otherwise.
  *
+ * Threading: b200pose_last_error() is per thread; a net / post object and the legacy process_paf surface serialise
+ * nothing themselves - use one object per host thread (or your own lock).  All work of a call is enqueued on the
+ * cuda_stream argument (plus the post object's private second stream for the person assembly and result copies).
+ *
  * Each declaration cites the reference interface it replaces (paths relative to /root/reference).
  * The reference-side bindings (ctypes) are shown in INTEGRATION.md.
  */

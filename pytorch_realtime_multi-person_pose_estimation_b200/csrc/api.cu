@@ -242,7 +242,7 @@ int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __n
     return 0;
 }
 
-int build_plan_bf16(b200pose_net* net, int n, int H, int W, bool split) {
+int build_plan_bf16(b200pose_net* net, int n, int H, int W, bool split, cudaStream_t st) {
     const size_t px1 = (size_t)n * H * W, px2 = px1 / 4, px4 = px1 / 16, px8 = px1 / 64;
     const int h = H / 8, w = W / 8;
     CU(net->t1.ensure(px1 * 64)); CU(net->t2.ensure(px2 * 64)); CU(net->t3.ensure(px2 * 128));
@@ -250,7 +250,9 @@ int build_plan_bf16(b200pose_net* net, int n, int H, int W, bool split) {
     CU(net->t6.ensure(px8 * 256)); CU(net->t7.ensure(px8 * 512)); CU(net->t8.ensure(px8 * 512));
     CU(net->t9.ensure(px8 * 256)); CU(net->cat.ensure(px8 * 192)); CU(net->bra.ensure(px8 * 256));
     CU(net->brb.ensure(px8 * 256)); CU(net->br512.ensure(px8 * 1024));
-    CU(cudaMemset(net->cat.p, 0, px8 * 192 * 2));
+    // pad lanes of the concat buffer must read as zero; on the caller's stream (a non-blocking stream is not ordered
+    // against the legacy default stream a plain cudaMemset would use)
+    CU(cudaMemsetAsync(net->cat.p, 0, px8 * 192 * 2, st));
     net->plan_split = split;
     net->lo_of.clear();
     if (split) {
@@ -259,7 +261,7 @@ int build_plan_bf16(b200pose_net* net, int n, int H, int W, bool split) {
         CU(net->l6.ensure(px8 * 256)); CU(net->l7.ensure(px8 * 512)); CU(net->l8.ensure(px8 * 512));
         CU(net->l9.ensure(px8 * 256)); CU(net->lcat.ensure(px8 * 192)); CU(net->lbra.ensure(px8 * 256));
         CU(net->lbrb.ensure(px8 * 256)); CU(net->lbr512.ensure(px8 * 1024));
-        CU(cudaMemset(net->lcat.p, 0, px8 * 192 * 2));
+        CU(cudaMemsetAsync(net->lcat.p, 0, px8 * 192 * 2, st));
         DevBuf<__nv_bfloat16>* hi[] = {&net->t1, &net->t2, &net->t3, &net->t4, &net->t5a, &net->t5b, &net->t6, &net->t7,
                                        &net->t8, &net->t9, &net->cat, &net->bra, &net->brb, &net->br512};
         DevBuf<__nv_bfloat16>* lo[] = {&net->l1, &net->l2, &net->l3, &net->l4, &net->l5a, &net->l5b, &net->l6, &net->l7,
@@ -309,7 +311,7 @@ int forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, i
     const int want = split ? B200POSE_MODE_BF16X3 : B200POSE_MODE_BF16;
     if (net->pn != n || net->pH != H || net->pW != W || net->pmode != want) {
         CU(cudaStreamSynchronize(st));
-        if (build_plan_bf16(net, n, H, W, split)) return 1;
+        if (build_plan_bf16(net, n, H, W, split, st)) return 1;
         net->pn = n; net->pH = H; net->pW = W; net->pmode = want;
     }
     CU(conv_first_launch(d_in, in_u8, net->d_w[0], net->d_b[0], net->t1.p, split ? net->l1.p : nullptr, n, H, W, st));
@@ -440,6 +442,7 @@ void b200pose_net_destroy(b200pose_net* net) {
 }
 
 int b200pose_net_set_tensor(b200pose_net* net, int index, const float* host_data, long count) {
+    if (!net || !host_data) return fail("set_tensor: null pointer");
     long dims[4];
     const int nd = b200pose_net_tensor_shape(index, dims);
     if (nd < 0) return fail("tensor index %d out of range", index);
@@ -454,6 +457,7 @@ int b200pose_net_set_tensor(b200pose_net* net, int index, const float* host_data
 }
 
 int b200pose_net_finalize(b200pose_net* net) {
+    if (!net) return fail("null net");
     CU(cudaSetDevice(net->device));
     for (int i = 0; i < B200POSE_NUM_TENSORS; ++i)
         if (!net->have[i]) return fail("state_dict tensor %d was never set", i);
@@ -1085,11 +1089,17 @@ int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, fl
     g_leg_humans.assign(p->hp_humans[p->cur], p->hp_humans[p->cur] + (size_t)g_leg_nh * kHumanFloats);
     return 0;
 }
+// The reference's getters index its vectors unchecked (pafprocess.cpp:196-218); out-of-range arguments return -1 / 0 here.
+static bool leg_human_ok(int human_id) { return human_id >= 0 && human_id < g_leg_nh; }
+static bool leg_cid_ok(int cid) { return cid >= 0 && (size_t)cid * 3 + 2 < g_leg_peaks.size(); }
 int get_num_humans(void) { return g_leg_nh; }
-int get_part_cid(int human_id, int part_id) { return (int)g_leg_humans[(size_t)human_id * kHumanFloats + 1 + 4 * part_id + 3]; }
-float get_score(int human_id) { return g_leg_humans[(size_t)human_id * kHumanFloats]; }
-int get_part_x(int cid) { return (int)g_leg_peaks[3 * (size_t)cid]; }
-int get_part_y(int cid) { return (int)g_leg_peaks[3 * (size_t)cid + 1]; }
-float get_part_score(int cid) { return g_leg_peaks[3 * (size_t)cid + 2]; }
+int get_part_cid(int human_id, int part_id) {
+    if (!leg_human_ok(human_id) || part_id < 0 || part_id >= 18) return -1;
+    return (int)g_leg_humans[(size_t)human_id * kHumanFloats + 1 + 4 * part_id + 3];
+}
+float get_score(int human_id) { return leg_human_ok(human_id) ? g_leg_humans[(size_t)human_id * kHumanFloats] : 0.f; }
+int get_part_x(int cid) { return leg_cid_ok(cid) ? (int)g_leg_peaks[3 * (size_t)cid] : -1; }
+int get_part_y(int cid) { return leg_cid_ok(cid) ? (int)g_leg_peaks[3 * (size_t)cid + 1] : -1; }
+float get_part_score(int cid) { return leg_cid_ok(cid) ? g_leg_peaks[3 * (size_t)cid + 2] : 0.f; }
 
 }  // extern "C"
