@@ -3,7 +3,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200pose.so")
+# B200POSE_LIB selects another build of the same library (tools/variants.py: compile-time tuning variants); there is
+# still no fallback of any kind - a missing file is an error.
+LIB_PATH = os.environ.get("B200POSE_LIB") or os.path.join(_HERE, "libb200pose.so")
 _lib = None
 
 c_float_p = ctypes.POINTER(ctypes.c_float)

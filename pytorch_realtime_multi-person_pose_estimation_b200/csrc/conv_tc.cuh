@@ -15,7 +15,10 @@ constexpr int kPatchPitch = 24;   // patch row pitch in pixels (16 + 6 halo, rou
 constexpr int kMaxKs = 7;
 constexpr int kPatchBytes = kPatchPitch * (kTileH + kMaxKs - 1) * 128;  // 67,584 B per 64-channel block
 constexpr int kBStageBytes = 128 * 128;                                 // up to N=128 rows of 64 bf16
-constexpr int kNumBStages = 5;
+#ifndef B2P_CONV_B_STAGES
+#define B2P_CONV_B_STAGES 5      // weight (B operand) pipeline depth; tools/variants.py builds the library with other values
+#endif
+constexpr int kNumBStages = B2P_CONV_B_STAGES;
 constexpr int kNumPatchStages = 2;
 constexpr int kConvTcThreads = 224;   // warps: 0 patch TMA, 1 MMA, 2-5 epilogue, 6 weight TMA
 constexpr int kConvTcSmemBytes = kNumPatchStages * kPatchBytes + kNumBStages * kBStageBytes + 1024 /*align*/ + 256;
