@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -173,6 +174,12 @@ struct b200pose_post {
     std::vector<float> h_px_s;
     std::vector<int> h_px, h_py;
     int hw_h = 0, hw_w = 0;
+    // EXPERIMENT (off unless B200POSE_POST_OVERLAP=1 when the object is created): peaks / limbs / assembly of run i all
+    // run on the second stream from a private copy of the maps, so they can overlap the convolutions of run i+1.
+    bool overlap = false;
+    DevBuf<float> ov_maps[2];                       // [heat | paf] copies, slot = run parity
+    cudaEvent_t ev_maps = nullptr, ev_ld[2] = {nullptr, nullptr};   // maps copied (st) / limbs done with a slot (s2)
+    bool have_ld[2] = {false, false};
 };
 
 namespace {
@@ -607,7 +614,11 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
         CU(cudaHostAlloc(&p->hp_status[b], (size_t)batch_cap * sizeof(int), cudaHostAllocDefault));
         CU(cudaHostAlloc(&p->hp_counts[b], (size_t)batch_cap * 18 * sizeof(int), cudaHostAllocDefault));
         CU(cudaHostAlloc(&p->hp_humans[b], (size_t)batch_cap * human_cap * kHumanFloats * sizeof(float), cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&p->ev_ld[b], cudaEventDisableTiming));
     }
+    CU(cudaEventCreateWithFlags(&p->ev_maps, cudaEventDisableTiming));
+    const char* ov = getenv("B200POSE_POST_OVERLAP");
+    p->overlap = ov && ov[0] == '1';
     *out = p;
     return 0;
 }
@@ -619,6 +630,9 @@ void b200pose_post_destroy(b200pose_post* p) {
     post_free(p->pb);
     p->d_heat.release(); p->d_paf.release();
     p->tta_in.release(); p->tta_out.release();
+    p->ov_maps[0].release(); p->ov_maps[1].release();
+    if (p->ev_maps) cudaEventDestroy(p->ev_maps);
+    for (int b = 0; b < 2; ++b) if (p->ev_ld[b]) cudaEventDestroy(p->ev_ld[b]);
     for (int b = 0; b < 2; ++b) {
         if (p->ev_fetch[b]) cudaEventDestroy(p->ev_fetch[b]);
         if (p->hp_nh[b]) cudaFreeHost(p->hp_nh[b]);
@@ -658,22 +672,42 @@ static int enqueue_assemble_and_fetch(b200pose_post* p, int n, cudaStream_t st) 
 static int post_run_dev(b200pose_post* p, const float* d_heat, const float* d_paf, int layout, int n, int h, int w,
                         float thresh, cudaStream_t st) {
     if (n > p->pb.batch_cap) return fail("batch %d exceeds post batch_cap %d", n, p->pb.batch_cap);
+    cudaStream_t ps = st;       // the stream peaks / limbs run on
+    const int slot = (int)(p->runs & 1);
+    if (p->overlap) {
+        // private copy of the maps (15 MB at batch 32) so that the next forward may overwrite the network's output
+        // buffers while this run's post-processing is still reading; everything after the copy runs on s2
+        const size_t eh = (size_t)n * 19 * h * w, ep = (size_t)n * 38 * h * w;
+        CU(p->ov_maps[slot].ensure(eh + ep));
+        if (p->have_ld[slot]) CU(cudaStreamWaitEvent(st, p->ev_ld[slot], 0));   // run i-2 is done with this slot
+        CU(cudaMemcpyAsync(p->ov_maps[slot].p, d_heat, eh * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(p->ov_maps[slot].p + eh, d_paf, ep * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaEventRecord(p->ev_maps, st));
+        CU(cudaStreamWaitEvent(p->s2, p->ev_maps, 0));
+        d_heat = p->ov_maps[slot].p;
+        d_paf = p->ov_maps[slot].p + eh;
+        ps = p->s2;
+    }
     // the previous run's assembly (second stream) still reads the peak / connection buffers this run overwrites
-    if (p->have_asm) CU(cudaStreamWaitEvent(st, p->ev_asm, 0));
+    if (p->have_asm) CU(cudaStreamWaitEvent(ps, p->ev_asm, 0));
     cudaError_t e;
     if (layout == 0) {
-        e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, (long)h * w, w, 1, h, w, thresh, st);
+        e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, (long)h * w, w, 1, h, w, thresh, ps);
         if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
-        e = post_limbs(p->pb, n, d_paf, (long)38 * h * w, (long)h * w, w, 1, 3, h * 8, w, h, st);
+        e = post_limbs(p->pb, n, d_paf, (long)38 * h * w, (long)h * w, w, 1, 3, h * 8, w, h, ps);
     } else {
-        e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, 1, (long)w * 19, 19, h, w, thresh, st);
+        e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, 1, (long)w * 19, 19, h, w, thresh, ps);
         if (e != cudaSuccess) return fail("post_peaks: %s", cudaGetErrorString(e));
-        e = post_limbs(p->pb, n, d_paf, (long)38 * h * w, 1, (long)w * 38, 38, 3, h * 8, w, h, st);
+        e = post_limbs(p->pb, n, d_paf, (long)38 * h * w, 1, (long)w * 38, 38, 3, h * 8, w, h, ps);
     }
     if (e != cudaSuccess) return fail("post_limbs: %s", cudaGetErrorString(e));
     g_launches += 2;
+    if (p->overlap) {
+        CU(cudaEventRecord(p->ev_ld[slot], ps));
+        p->have_ld[slot] = true;
+    }
     p->hw_h = h; p->hw_w = w;
-    return enqueue_assemble_and_fetch(p, n, st);
+    return enqueue_assemble_and_fetch(p, n, ps);
 }
 
 int b200pose_post_run(b200pose_post* p, const float* heat, const float* paf, int on_device, int layout, int n, int h,

@@ -4,6 +4,7 @@
 // the design goal is: everything stays on the device, one block per (image, part) / (image, limb) / image, warp
 // shuffles for ordered compaction and arg-max, shared memory for the plane / candidate keys.
 #include <cstdio>
+#include <cstdlib>
 
 #include "postprocess.cuh"
 
@@ -924,7 +925,9 @@ cudaError_t post_limbs(const PostBuffers& pb, int batch, const float* paf, long 
     if (pb.cand_smem_cap != kSmemRange) return cudaErrorInvalidValue;
     size_t smem = kSmemRange * sizeof(unsigned long long) + 2 * (kSmemRange + 2) * sizeof(int32_t);
     int in_smem = 0;
-    if (shift == 3 && (size_t)2 * lw * lh * sizeof(float) <= 96 * 1024) {
+    // EXPERIMENT switch (round-2 co-residency study): keep the PAF planes in global memory / L2 to shrink the footprint
+    static const bool paf_global = [] { const char* v = getenv("B200POSE_LIMBS_PAF_GLOBAL"); return v && v[0] == '1'; }();
+    if (!paf_global && shift == 3 && (size_t)2 * lw * lh * sizeof(float) <= 96 * 1024) {
         in_smem = 1;
         smem += (size_t)2 * lw * lh * sizeof(float);
     }
