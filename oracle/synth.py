@@ -70,3 +70,91 @@ def noise_maps(seed, h=46, w=46, heat_scale=0.45, paf_scale=0.6):
     heat = (rs.standard_normal((h, w, 19)) * heat_scale).astype(np.float32)
     paf = (rs.standard_normal((h, w, 38)) * paf_scale).astype(np.float32)
     return heat, paf
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fuzz scenarios for the pafprocess stage (joint list + low-resolution PAF maps, no NMS involved): used to compare the
+# reference's compiled pafprocess.cpp with the product's cores on inputs the stick-figure fixtures do not reach
+# (cross links between persons, duplicated peaks on one pixel, exact score ties, masked fields).
+_LIMBS = [(1, 2), (1, 5), (2, 3), (3, 4), (5, 6), (6, 7), (1, 8), (8, 9), (9, 10), (1, 11), (11, 12), (12, 13), (1, 0),
+          (0, 14), (14, 16), (0, 15), (15, 17), (2, 16), (5, 17)]                       # pafprocess.h:21-24
+_PAFCH = [(12, 13), (20, 21), (14, 15), (16, 17), (22, 23), (24, 25), (0, 1), (2, 3), (4, 5), (6, 7), (8, 9), (10, 11),
+          (28, 29), (30, 31), (34, 35), (32, 33), (36, 37), (18, 19), (26, 27)]           # pafprocess.h:16-19
+
+
+def fuzz_field(rs, h, w, kind):
+    """Random peaks (kind: 'uniform' | 'cluster' | 'ties') + per-limb (nearly) constant direction fields."""
+    maxp = int(rs.choice([1, 2, 3, 5, 8]))
+    rows = []
+    centers = rs.randint(8, min(h, w) * 8 - 8, (int(rs.randint(1, 6)), 2))
+    for part in range(18):
+        for _ in range(int(rs.randint(0, maxp + 1))):
+            if kind in ("cluster", "ties") and rs.rand() < 0.8:
+                c = centers[rs.randint(len(centers))]
+                spread = 3 if kind == "ties" else 40
+                x = int(np.clip(c[0] + rs.randint(-spread, spread + 1), 0, w * 8 - 1))
+                y = int(np.clip(c[1] + rs.randint(-spread, spread + 1), 0, h * 8 - 1))
+            else:
+                x, y = int(rs.randint(0, w * 8)), int(rs.randint(0, h * 8))
+            rows.append((x, y, float(np.float32(rs.choice([0.2, 0.5, 0.9, rs.rand()]))), 0, part))
+    jl = np.array(rows, np.float32).reshape(-1, 5)
+    jl[:, 3] = np.arange(len(jl))
+    paf = np.zeros((h, w, 38), np.float32)
+    for ch in range(0, 38, 2):
+        ang = rs.choice([0, np.pi / 2, np.pi, 3 * np.pi / 2, np.pi / 4]) if kind == "ties" else rs.rand() * 2 * np.pi
+        mag = rs.choice([0.3, 0.6, 1.0])
+        noise = 0.0 if kind == "ties" else 0.3
+        paf[:, :, ch] = np.cos(ang) * mag + noise * rs.randn(h, w)
+        paf[:, :, ch + 1] = np.sin(ang) * mag + noise * rs.randn(h, w)
+        if rs.rand() < 0.3:
+            paf[:, :, ch:ch + 2] *= (rs.rand(h, w, 1) < 0.7)
+    return jl, np.ascontiguousarray(paf.astype(np.float32))
+
+
+def fuzz_persons(rs, h, w):
+    """1-6 loosely person-shaped peak sets with their true limbs drawn into the PAF maps, random cross links between
+    persons (ambiguous assignments, merges of partial persons) and duplicated peaks (exact score ties)."""
+    K = int(rs.randint(1, 7))
+    pts = {}
+    for k in range(K):
+        c = rs.randint(40, min(h, w) * 8 - 40, 2)
+        sc = rs.randint(10, 45)
+        for part in range(18):
+            if rs.rand() < 0.85:
+                pts[(k, part)] = (int(np.clip(c[0] + rs.randint(-sc, sc + 1), 0, w * 8 - 1)),
+                                  int(np.clip(c[1] + rs.randint(-sc, sc + 1), 0, h * 8 - 1)))
+    rows = []
+    for part in range(18):
+        for k in range(K):
+            if (k, part) in pts:
+                x, y = pts[(k, part)]
+                rows.append((x, y, float(np.float32(rs.choice([0.3, 0.6, 0.95]))), 0, part))
+                if rs.rand() < 0.15:
+                    rows.append((x + int(rs.randint(0, 2)), y, float(np.float32(0.6)), 0, part))
+    jl = np.array(rows, np.float32).reshape(-1, 5)
+    jl[:, 3] = np.arange(len(jl))
+    paf = np.zeros((h, w, 38), np.float32)
+
+    def draw(a, b, chx, chy, mag):
+        ax, ay, bx, by = a[0] / 8.0, a[1] / 8.0, b[0] / 8.0, b[1] / 8.0
+        d = np.array([bx - ax, by - ay])
+        nrm = np.linalg.norm(d)
+        if nrm < 1e-6:
+            return
+        u = d / nrm
+        for t in np.linspace(0, 1, int(nrm * 2) + 2):
+            px, py = ax + t * d[0], ay + t * d[1]
+            for ox in (-1, 0, 1):
+                for oy in (-1, 0, 1):
+                    xi, yi = int(round(px)) + ox, int(round(py)) + oy
+                    if 0 <= xi < w and 0 <= yi < h:
+                        paf[yi, xi, chx] = u[0] * mag
+                        paf[yi, xi, chy] = u[1] * mag
+    for l, (pa, pb) in enumerate(_LIMBS):
+        for k in range(K):
+            if (k, pa) in pts and (k, pb) in pts and rs.rand() < 0.9:
+                draw(pts[(k, pa)], pts[(k, pb)], _PAFCH[l][0], _PAFCH[l][1], float(rs.choice([0.5, 0.8, 1.0])))
+            k2 = int(rs.randint(K))
+            if k2 != k and (k, pa) in pts and (k2, pb) in pts and rs.rand() < 0.35:
+                draw(pts[(k, pa)], pts[(k2, pb)], _PAFCH[l][0], _PAFCH[l][1], float(rs.choice([0.5, 0.8, 1.0])))
+    return jl, np.ascontiguousarray(paf)
