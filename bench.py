@@ -109,10 +109,12 @@ def run_ours(args):
     # Frames are uint8 HWC BGR (what cv2.imread / crop_with_factor hand to get_outputs); rtpose_preprocess is fused
     # into the first convolution.  10 rotating device batches (10 x 13 MB > 126 MB L2) + 2 pinned host batches.
     g = torch.Generator().manual_seed(1234 + rank)
-    host = [torch.randint(0, 256, (BATCH, H, W, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    # --raw N: the frames are N x N "camera" frames and crop_with_factor (resize to 368 x 368) runs on the device too
+    SH = SW = args.raw if args.raw else H
+    host = [torch.randint(0, 256, (BATCH, SH, SW, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
     # enough rotating device batches that one full rotation exceeds the 126 MB L2 (10 at batch 32)
-    n_rot = max(10, -(-130_000_000 // (BATCH * H * W * 3)))
-    devin = [torch.randint(0, 256, (BATCH, H, W, 3), generator=g, dtype=torch.uint8).to(dev) for i in range(n_rot)]
+    n_rot = max(10, -(-130_000_000 // (BATCH * SH * SW * 3)))
+    devin = [torch.randint(0, 256, (BATCH, SH, SW, 3), generator=g, dtype=torch.uint8).to(dev) for i in range(n_rot)]
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
@@ -121,7 +123,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    infer_u8 = eng.infer_flip_async_u8 if args.flip else eng.infer_async_u8
+    if args.raw:
+        def infer_u8(ptr, on_device, n, h_, w_, thresh, stream):
+            return eng.infer_raw_async_u8(ptr, on_device, n, SH, SW, H, 8, thresh, args.flip, stream)
+    else:
+        infer_u8 = eng.infer_flip_async_u8 if args.flip else eng.infer_async_u8
 
     def step_device(i):
         infer_u8(devin[i % n_rot].data_ptr(), True, BATCH, H, W, 0.1, sptr)
@@ -226,12 +232,13 @@ def run_ours(args):
                                % (BATCH, " (BASELINE.json configs[2]; configs[3] when n_gpus=8)" if BATCH == 32 and not args.flip
                                   else (", left/right flip test-time averaging on the device (2 forwards per frame)" if args.flip else "")),
                    "global_batch": BATCH * world, "weights": "He-normal seed 1234 (random init)",
-                   "input": "uint8 HWC BGR frames, rtpose_preprocess fused on the device",
+                   "input": ("uint8 HWC BGR %dx%d frames, crop_with_factor (bilinear resize to 368x368) and rtpose_preprocess on "
+                             "the device" % (SH, SW)) if args.raw else "uint8 HWC BGR frames, rtpose_preprocess fused on the device",
                    "l2": "inputs rotate over %d device batches (%d MB > 126 MB L2); ~%d MB of activations per step"
-                         % (n_rot, n_rot * BATCH * H * W * 3 // 1000000, 44 * BATCH * (2 if args.flip else 1)),
+                         % (n_rot, n_rot * BATCH * SH * SW * 3 // 1000000, 44 * BATCH * (2 if args.flip else 1)),
                    "parallelism": "dp%d (frames sharded, one NCCL weight broadcast)" % world,
                    "post_status_bits": int(st0)},
-        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * H * W * world,
+        "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * SH * SW * world,
                 "d2h_bytes_per_step": (int(np.mean(d2h_bytes)) if d2h_bytes else 0) * world,   # rank 0's count x ranks
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -327,6 +334,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step (the headline config is 32)")
     ap.add_argument("--flip", action="store_true", help="left/right flip test-time averaging (2 forwards per frame)")
+    ap.add_argument("--raw", type=int, default=0, metavar="N",
+                    help="feed N x N raw frames and run crop_with_factor (resize to 368 x 368) on the device as well")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global BATCH
