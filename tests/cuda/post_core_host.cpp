@@ -16,6 +16,7 @@ static const int LIMB_PAF[19][2] = B2P_LIMB_PAF_TABLES;
 
 static std::vector<float> g_out;   // per human: score, then 18 x (x, y, peak score, cid)  (cid < 0 = missing)
 static int g_degraded = 0, g_ties = 0, g_sort_mismatch = 0;
+static long g_cand_total = 0, g_cand_needed = 0;   // statistics: candidates per frame / candidates up to the last accepted one
 
 extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by part*/, int h_up, const float* paf,
                             long sc, long sy, long sx, int shift, int list_cap_stress) {
@@ -44,6 +45,7 @@ extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by p
     std::vector<float> cs[19];
     g_ties = 0;
     g_sort_mismatch = 0;
+    g_cand_total = g_cand_needed = 0;
     int total_conn = 0;
     for (int l = 0; l < 19; ++l) {
         const int pa = LIMB_PARTS[l][0], pb = LIMB_PARTS[l][1];
@@ -77,6 +79,19 @@ extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by p
                               cb[l].data(), cs[l].data());
         ca[l].resize(nc); cb[l].resize(nc); cs[l].resize(nc);
         total_conn += nc;
+        {   // how far down the sorted list does the greedy rule have to look?  (until min(na, nb) connections exist, else
+            // to the end) - the potential of sorting lazily, left to right
+            std::vector<char> fa(na, 0), fb(nb, 0);
+            long last = (long)sorted.size();
+            int made = 0;
+            for (size_t i = 0; i < sorted.size(); ++i) {
+                const uint32_t pair = (uint32_t)sorted[i];
+                const int a = pair / nb, b = pair % nb;
+                if (!fa[a] && !fb[b]) { fa[a] = fb[b] = 1; if (++made == maxc) { last = (long)i + 1; break; } }
+            }
+            g_cand_total += (long)sorted.size();
+            g_cand_needed += last;
+        }
     }
     std::vector<float> rows((size_t)(total_conn + 1) * kRowFloats);
     std::vector<uint8_t> alive(total_conn + 1, 0), list_n(n_peaks + 1, 0);
@@ -108,6 +123,8 @@ extern "C" int core_process(int n_peaks, const float* peaks /*[P][5] sorted by p
 extern "C" const float* core_result() { return g_out.data(); }
 extern "C" int core_degraded() { return g_degraded; }
 extern "C" int core_ties() { return g_ties; }
+extern "C" long core_cand_total() { return g_cand_total; }
+extern "C" long core_cand_needed() { return g_cand_needed; }
 extern "C" int core_sort_mismatch() { return g_sort_mismatch; }
 // direct test hook: sort `n` keys with both formulations, return 0 when identical
 extern "C" int core_sort_check(uint64_t* keys, int n, uint64_t* out) {
