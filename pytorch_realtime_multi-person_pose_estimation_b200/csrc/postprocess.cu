@@ -201,6 +201,12 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* scra
 // Together this is exactly __introsort_loop + __final_insertion_sort, including the order of equal keys.
 constexpr int kSortQ = 128, kSortLocal = 40, kLimbWarps = kLimbThreads / 32;
 constexpr int kSmemRange = B2P_SMEM_RANGE, kWarpRange = 512, kBigStack = 80;
+// Per-warp rank tables of the warp phase live in the (then idle) block-phase scratch of 2 x (kSmemRange + 2) int32:
+// two uint16 tables of kWarpRankRange entries per warp.  512 for the default 4096-key shared ranges; smaller shared
+// ranges (tools/variants.py) shrink the tables, longer ranges then take the chunked warp_partition.
+constexpr int kScratchBytes = 2 * (kSmemRange + 2) * (int)sizeof(int32_t);
+constexpr int kWarpRankRange = kScratchBytes / (kLimbWarps * 4) >= 512 ? 512 : (kScratchBytes / (kLimbWarps * 4) >= 256 ? 256 : 128);
+static_assert(kLimbWarps * 2 * kWarpRankRange * (int)sizeof(uint16_t) <= kScratchBytes, "warp rank tables do not fit the scratch");
 #ifndef B2P_SEQ_RANGE
 #define B2P_SEQ_RANGE 16
 #endif
@@ -219,7 +225,7 @@ struct SortShared {
     unsigned long long scan2[kLimbThreads / 32 + 1];
     int ksum;
     unsigned char wscr[kLimbWarps][64];     // rank -> lane tables of warp_partition
-    uint16_t* wtab;                         // kLimbWarps x 1024 uint16: per-warp rank -> position tables (warp phase)
+    uint16_t* wtab;                         // kLimbWarps x 2 x kWarpRankRange uint16: per-warp rank -> position tables
     unsigned long long* dbg;                // optional diagnostics counters
     // per-warp batch of small ranges (<= kSeqRange keys): sorted one range per lane by seq_sort_range()
     int bn[kLimbWarps];
@@ -347,8 +353,10 @@ __device__ void warp_descend(uint64_t* v, int f, int l, int d, SortShared& sh) {
             return;
         }
         --d;
-        const int cut = (l - f <= 512) ? rank_partition<uint16_t, 1>(v, f, l, sh.wtab + warp * 1024, sh.wtab + warp * 1024 + 512, sh)
-                                       : (int)warp_partition(v, f, l, sh.wscr[warp]);
+        const int cut = (l - f <= kWarpRankRange)
+                            ? rank_partition<uint16_t, 1>(v, f, l, sh.wtab + warp * 2 * kWarpRankRange,
+                                                          sh.wtab + warp * 2 * kWarpRankRange + kWarpRankRange, sh)
+                            : (int)warp_partition(v, f, l, sh.wscr[warp]);
         if (l - cut > kSeqRange) {
             if (lane == 0) {
                 __threadfence_block();
