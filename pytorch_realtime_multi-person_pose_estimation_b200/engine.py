@@ -152,16 +152,24 @@ class NativePost:
 
 
 def humans_to_dicts(rows, width, height):
-    """[(score, {part: (x/width, y/height, peak score)})] - the content paf_to_pose_cpp puts into Human objects."""
+    """[(score, {part: (x/width, y/height, peak score)})] - the content paf_to_pose_cpp puts into Human objects.
+    Conversions are done in bulk (float32 -> Python float, i.e. double, then the divisions in double exactly like the
+    reference's `float(x) / W`); the per-person dictionaries are the only Python-level loop left."""
+    rows = np.asarray(rows, dtype=np.float32).reshape(-1, nat.HUMAN_FLOATS)
+    if rows.shape[0] == 0:
+        return []
+    body = rows[:, 1:].reshape(-1, 18, 4).astype(np.float64)
+    xs = (body[:, :, 0] / width).tolist()
+    ys = (body[:, :, 1] / height).tolist()
+    ss = body[:, :, 2].tolist()
+    present = (body[:, :, 3] >= 0).tolist()
+    scores = rows[:, 0].astype(np.float64).tolist()
     out = []
-    for r in rows:
-        parts = {}
-        for p in range(18):
-            x, y, s, cid = r[1 + 4 * p: 5 + 4 * p]
-            if cid >= 0:
-                parts[p] = (float(x) / width, float(y) / height, float(s))
+    for k in range(len(scores)):
+        pr, x, y, sc = present[k], xs[k], ys[k], ss[k]
+        parts = {p: (x[p], y[p], sc[p]) for p in range(18) if pr[p]}
         if parts:
-            out.append((float(r[0]), parts))
+            out.append((scores[k], parts))
     return out
 
 
@@ -268,6 +276,18 @@ class PoseEngine:
         if check:
             self.post.check_status(n)
         return [humans_to_dicts(self.post.humans(i), W, H) for i in range(n)]
+
+    def fetch_arrays(self, check=True, ticket=None):
+        """Like fetch() but without building Python objects: per image a float32 array [k, 73] with rows
+        (score, 18 x (x, y, peak score, peak id | -1)), x / y in pixels of the (padded) network input."""
+        n, H, W = self._last
+        if ticket is None:
+            self.post.sync()
+        else:
+            self.post.select(ticket)
+        if check:
+            self.post.check_status(n)
+        return [self.post.humans(i) for i in range(n)]
 
     def infer_batch(self, images, thresh=0.1, flip=False):
         """images: uint8 numpy [n,H,W,3] (BGR frames, preprocessing fused on the device), float32 numpy [n,3,H,W]
