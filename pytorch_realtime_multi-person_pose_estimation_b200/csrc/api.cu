@@ -139,6 +139,19 @@ struct b200pose_net {
     std::vector<ConvTcArgs> plan;
     std::vector<double> plan_flops;   // algorithmic FLOPs per launch of `plan`
     bool plan_split = false;          // the plan was built for the split-precision (bf16x3) mode
+    // EXPERIMENT (off unless B200POSE_PLAN_CACHE=1 when the net is created): keep the plans of other (n, H, W, mode)
+    // keys so that alternating shapes (multi-scale, mixed frame sizes) do not re-encode 51 tensor maps and synchronise
+    // the stream.  An entry is valid while the activation buffers it points into have not been reallocated.
+    struct PlanEntry {
+        int n, H, W, mode;
+        bool split;
+        std::vector<ConvTcArgs> plan;
+        std::vector<double> flops;
+        std::vector<const void*> buffers;
+    };
+    bool plan_cache_on = false;
+    int kn = 0, kH = 0, kW = 0, kmode = -1;      // key of the plan currently held in `plan`
+    std::vector<PlanEntry> plan_cache;
     DevBuf<__nv_bfloat16> t1, t2, t3, t4, t5a, t5b, t6, t7, t8, t9, cat, bra, brb, br512;
     // residual ("lo") planes of the same buffers, split-precision mode only
     DevBuf<__nv_bfloat16> l1, l2, l3, l4, l5a, l5b, l6, l7, l8, l9, lcat, lbra, lbrb, lbr512;
@@ -314,11 +327,52 @@ int build_plan_bf16(b200pose_net* net, int n, int H, int W, bool split, cudaStre
     return 0;
 }
 
+std::vector<const void*> plan_buffers(const b200pose_net* net) {
+    std::vector<const void*> v = {net->t1.p, net->t2.p, net->t3.p, net->t4.p, net->t5a.p, net->t5b.p, net->t6.p, net->t7.p,
+                                  net->t8.p, net->t9.p, net->cat.p, net->bra.p, net->brb.p, net->br512.p,
+                                  net->l1.p, net->l2.p, net->l3.p, net->l4.p, net->l5a.p, net->l5b.p, net->l6.p, net->l7.p,
+                                  net->l8.p, net->l9.p, net->lcat.p, net->lbra.p, net->lbrb.p, net->lbr512.p};
+    for (const auto& b : net->out_f32) v.push_back(b.p);
+    return v;
+}
+
+// plan cache (experiment): returns true when a valid plan for the key was swapped into net->plan
+bool plan_cache_swap(b200pose_net* net, int n, int H, int W, int want) {
+    if (net->kmode >= 0 && !net->plan.empty()) {      // stash the plan we hold
+        b200pose_net::PlanEntry* slot = nullptr;
+        for (auto& e : net->plan_cache)
+            if (e.n == net->kn && e.H == net->kH && e.W == net->kW && e.mode == net->kmode) slot = &e;
+        if (!slot) {
+            if (net->plan_cache.size() >= 32) net->plan_cache.erase(net->plan_cache.begin());
+            net->plan_cache.emplace_back();
+            slot = &net->plan_cache.back();
+        }
+        slot->n = net->kn; slot->H = net->kH; slot->W = net->kW; slot->mode = net->kmode; slot->split = net->plan_split;
+        slot->plan.swap(net->plan);
+        slot->flops.swap(net->plan_flops);
+        slot->buffers = plan_buffers(net);
+        net->plan.clear(); net->plan_flops.clear();
+        net->kmode = -1;
+    }
+    for (auto& e : net->plan_cache)
+        if (e.n == n && e.H == H && e.W == W && e.mode == want && !e.plan.empty() && e.buffers == plan_buffers(net)) {
+            net->plan.swap(e.plan);
+            net->plan_flops.swap(e.flops);
+            net->plan_split = e.split;
+            net->kn = n; net->kH = H; net->kW = W; net->kmode = want;
+            return true;
+        }
+    return false;
+}
+
 int forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, int W, cudaStream_t st, bool split) {
     const int want = split ? B200POSE_MODE_BF16X3 : B200POSE_MODE_BF16;
     if (net->pn != n || net->pH != H || net->pW != W || net->pmode != want) {
-        CU(cudaStreamSynchronize(st));
-        if (build_plan_bf16(net, n, H, W, split, st)) return 1;
+        if (!(net->plan_cache_on && plan_cache_swap(net, n, H, W, want))) {
+            CU(cudaStreamSynchronize(st));
+            if (build_plan_bf16(net, n, H, W, split, st)) return 1;
+            net->kn = n; net->kH = H; net->kW = W; net->kmode = want;
+        }
         net->pn = n; net->pH = H; net->pW = W; net->pmode = want;
     }
     CU(conv_first_launch(d_in, in_u8, net->d_w[0], net->d_b[0], net->t1.p, split ? net->l1.p : nullptr, n, H, W, st));
@@ -425,6 +479,8 @@ int b200pose_net_create(b200pose_net** out, int cuda_device) {
     net->host_w.resize(kNumConvs);
     net->host_b.resize(kNumConvs);
     net->have.assign(B200POSE_NUM_TENSORS, false);
+    const char* pc = getenv("B200POSE_PLAN_CACHE");
+    net->plan_cache_on = pc && pc[0] == '1';
     *out = net;
     return 0;
 }
@@ -497,6 +553,9 @@ int b200pose_net_finalize(b200pose_net* net) {
         }
     net->pn = net->pH = net->pW = 0;
     net->pmode = -1;
+    net->plan_cache.clear();      // cached plans point at the previous packed weights
+    net->plan.clear(); net->plan_flops.clear();
+    net->kmode = -1;
     net->finalized = true;
     return 0;
 }
