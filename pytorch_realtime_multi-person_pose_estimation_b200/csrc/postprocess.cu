@@ -600,8 +600,23 @@ __device__ int greedy_segmented(const uint64_t* keys, int n, int nb, uint32_t* u
     return *s_nc;
 }
 
+// B2P_LIMBS_PERSISTENT (tools/variants.py, co-residency study): instead of one block per (image, limb) the grid is a
+// fixed number of blocks (about one per SM) that pull (image, limb-rank) items from an atomic counter (pb.dbg[15], zeroed
+// by the host) in the same longest-job-first order.  At most one such block then sits next to a conv CTA on an SM.
+#ifndef B2P_LIMBS_PERSISTENT
+#define B2P_LIMBS_PERSISTENT 0
+#endif
+#if B2P_LIMBS_PERSISTENT
+#define B2P_ITEM_DONE continue
+#else
+#define B2P_ITEM_DONE return
+#endif
 __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up, int lw,
-                                                             int lh, int paf_in_smem) {
+                                                             int lh, int paf_in_smem
+#if B2P_LIMBS_PERSISTENT
+                                                             , int batch
+#endif
+                                                             ) {
     // dynamic smem: [kSmemRange keys][2 x (kSmemRange + 2) int32 partition scratch][optional 2 PAF planes]
     extern __shared__ unsigned long long sm_keys[];
     int32_t* sm_scr = reinterpret_cast<int32_t*>(sm_keys + kSmemRange);
@@ -611,8 +626,19 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     __shared__ SortShared s_sort;
     // Longest-job-first: grid = (image, rank); block `rank` of an image takes the limb with the rank-th largest number
     // of (a, b) pairs, so across the whole grid the heavy limbs are scheduled before the light ones (shorter tail).
-    const int img = blockIdx.x, tid = threadIdx.x;
-    int limb = blockIdx.y;
+    const int tid = threadIdx.x;
+#if B2P_LIMBS_PERSISTENT
+    __shared__ int s_item;
+    for (;;) {
+    __syncthreads();                                  // the previous item's shared state is dead
+    if (tid == 0) s_item = (int)atomicAdd(pb.dbg + 15, 1ull);
+    __syncthreads();
+    if (s_item >= batch * kNumLimb) return;
+    const int img = s_item % batch, rank_y = s_item / batch;
+#else
+    const int img = blockIdx.x, rank_y = blockIdx.y;
+#endif
+    int limb = rank_y;
     {
         int my_pairs[kNumLimb];
 #pragma unroll
@@ -622,7 +648,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
             int rank = 0;
             for (int m = 0; m < kNumLimb; ++m)
                 rank += (my_pairs[m] > my_pairs[l]) || (my_pairs[m] == my_pairs[l] && m < l);
-            if (rank == (int)blockIdx.y) limb = l;
+            if (rank == rank_y) limb = l;
         }
     }
     const int pa = c_limb_parts[limb][0], pbp = c_limb_parts[limb][1];
@@ -631,7 +657,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     int* out_cnt = pb.conn_cnt + img * kNumLimb + limb;
     if (na == 0 || nb == 0) {
         if (tid == 0) *out_cnt = 0;
-        return;
+        B2P_ITEM_DONE;
     }
     const int* ax = pb.peak_x + ((long)img * kNumPart + pa) * cap;
     const int* ay = pb.peak_y + ((long)img * kNumPart + pa) * cap;
@@ -668,7 +694,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
                 atomicOr(&pb.status[img], 2);
                 *out_cnt = 0;
             }
-            return;
+            B2P_ITEM_DONE;
         }
         keys = pb.pool + s_pool_base;
         __syncthreads();
@@ -703,7 +729,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     }
     if (n == 0) {
         if (tid == 0) *out_cnt = 0;
-        return;
+        B2P_ITEM_DONE;
     }
     if (npairs > kSmemRange && n > kSmemRange) {   // rank -> position scratch of the global-level partitions: n + 2 entries
         if (tid == 0) s_pool_base = (long)atomicAdd(pb.pool_cursor, (unsigned long long)n + 2);
@@ -713,7 +739,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
                 atomicOr(&pb.status[img], 2);
                 *out_cnt = 0;
             }
-            return;
+            B2P_ITEM_DONE;
         }
         posA = reinterpret_cast<int32_t*>(pb.pool + s_pool_base);
         posB = posA + n + 2;
@@ -744,6 +770,9 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
             }
         }
     }
+#if B2P_LIMBS_PERSISTENT
+    }
+#endif
 }
 
 // ------------------------------------------------------------------ assembly
@@ -944,7 +973,13 @@ cudaError_t post_limbs(const PostBuffers& pb, int batch, const float* paf, long 
         B2P_TRY(cudaFuncSetAttribute(limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
+#if B2P_LIMBS_PERSISTENT
+    static const int grid = [] { const char* v = getenv("B200POSE_LIMBS_GRID"); const int g = v ? atoi(v) : 148; return g > 0 ? g : 148; }();
+    B2P_TRY(cudaMemsetAsync(pb.dbg + 15, 0, sizeof(unsigned long long), s));
+    limbs_kernel<<<grid < batch * kNumLimb ? grid : batch * kNumLimb, kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem, batch);
+#else
     limbs_kernel<<<dim3(batch, kNumLimb), kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem);
+#endif
     return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ for v in $names; do
       > gpurun_out/variants/$v.json 2>> gpurun_out/variants/$v.log
 done
 # overlap experiments: the same libraries with the post-processing on the second stream
-for v in base cores; do
+for v in base persist cores; do
   lib=$PWD/build/variants/libb200pose_$v.so
   [ -f "$lib" ] || continue
   extra=""; [ "$v" = cores ] && extra="B200POSE_LIMBS_PAF_GLOBAL=1"
