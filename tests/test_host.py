@@ -335,7 +335,8 @@ def test_cubic_resize_device_core_on_host_matches_oracle(built):
     lib.core_resize_cubic.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3 + [ctypes.c_void_p] + [ctypes.c_int] * 2
     rs = np.random.RandomState(13)
     cases = [(23, 23, 46, 46, 19), (69, 69, 46, 46, 38), (92, 92, 46, 46, 19), (6, 9, 12, 16, 38), (24, 33, 12, 16, 19),
-             (46, 53, 46, 53, 38)] + [tuple(int(v) for v in rs.randint(3, 80, 4)) + (int(rs.choice([1, 19, 38])),) for _ in range(20)]
+             (46, 53, 46, 53, 38), (1, 1, 4, 4, 19), (2, 1, 3, 5, 38), (1, 7, 9, 2, 1)] + \
+            [tuple(int(v) for v in rs.randint(3, 80, 4)) + (int(rs.choice([1, 19, 38])),) for _ in range(20)]
     for (h, w, dh, dw, c) in cases:
         src = rs.randn(h, w, c).astype(np.float32)
         out = np.empty((dh, dw, c), np.float32)
