@@ -58,6 +58,14 @@ int b200pose_net_forward(b200pose_net* net, const float* input, int input_on_dev
  * into the first convolution's load: 4x less H2D traffic, no fp32 staging. */
 int b200pose_net_forward_u8(b200pose_net* net, const unsigned char* images, int input_on_device, int n, int H, int W,
                             int mode, float* const* outputs, int outputs_on_device, void* cuda_stream);
+/* Normalisation the uint8 entry points (b200pose_net_forward_u8, b200pose_infer_u8*, b200pose_infer_raw_u8*) fuse into
+ * the first convolution: get_outputs' `preprocess` argument (evaluate/coco_eval.py:92-100; functions in
+ * lib/datasets/preprocessing.py:16-86).  Default B200POSE_PRE_RTPOSE.  Bit-identical to the numpy functions. */
+#define B200POSE_PRE_RTPOSE 1      /* x/256 - 0.5                                   */
+#define B200POSE_PRE_VGG 2         /* BGR -> RGB, /255, (x - mean) / std            */
+#define B200POSE_PRE_INCEPTION 3   /* BGR -> RGB, x/128 - 1                         */
+#define B200POSE_PRE_SSD 4         /* x - (123, 117, 104) on (B, G, R)              */
+int b200pose_net_set_preprocess(b200pose_net* net, int preprocess);
 /* Measurement hook: re-runs the launch list of the last bf16 forward (conv1_1 + 51 tensor-core launches) with a CUDA
  * event pair around every launch; fills per-launch milliseconds and ALGORITHMIC FLOPs (2 x MACs of the unpadded
  * convolution).  Returns the number of launches, < 0 on error. */

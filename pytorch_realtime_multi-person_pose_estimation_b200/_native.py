@@ -13,6 +13,7 @@ NUM_TENSORS = 184
 HUMAN_FLOATS = 73
 MODE_BF16, MODE_FP32, MODE_BF16X3 = 0, 1, 2
 MODES = {"bf16": MODE_BF16, "fp32": MODE_FP32, "bf16x3": MODE_BF16X3}
+PREPROCESS = {"rtpose": 1, "vgg": 2, "inception": 3, "ssd": 4}      # get_outputs' `preprocess` names
 
 
 class B200PoseError(RuntimeError):
@@ -39,6 +40,7 @@ def lib():
         "b200pose_net_finalize": ([vp], ci),
         "b200pose_net_forward": ([vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(vp), ci, vp], ci),
         "b200pose_net_forward_u8": ([vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(vp), ci, vp], ci),
+        "b200pose_net_set_preprocess": ([vp, ci], ci),
         "b200pose_net_profile": ([vp, vp, vp, ci, vp], ci),
         "b200pose_net_last_maps": ([vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ci), ctypes.POINTER(ci),
                                     ctypes.POINTER(ci)], ci),
@@ -81,7 +83,7 @@ def lib():
 
 EXPORTED = ["b200pose_last_error", "b200pose_version", "b200pose_launch_count", "b200pose_net_create",
             "b200pose_net_destroy", "b200pose_net_tensor_shape", "b200pose_net_set_tensor", "b200pose_net_finalize",
-            "b200pose_net_forward", "b200pose_net_forward_u8", "b200pose_net_profile", "b200pose_net_last_maps", "b200pose_post_create", "b200pose_post_destroy",
+            "b200pose_net_forward", "b200pose_net_forward_u8", "b200pose_net_set_preprocess", "b200pose_net_profile", "b200pose_net_last_maps", "b200pose_post_create", "b200pose_post_destroy",
             "b200pose_post_run", "b200pose_post_sync", "b200pose_post_last_ticket", "b200pose_post_select", "b200pose_post_debug", "b200pose_post_num_humans", "b200pose_post_status",
             "b200pose_post_get_humans", "b200pose_post_get_peaks", "b200pose_infer", "b200pose_infer_u8", "b200pose_flip_merge", "b200pose_infer_flip",
             "b200pose_infer_u8_flip", "b200pose_crop_geometry", "b200pose_net_crop_with_factor",

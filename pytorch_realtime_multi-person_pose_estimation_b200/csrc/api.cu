@@ -163,6 +163,7 @@ struct b200pose_net {
     const void* last_in = nullptr;    // device pointer of the last forward's input (profiling hook)
     int last_in_u8 = 0;
     DevBuf<unsigned char> in_stage_u8;
+    int preprocess = 1;                // normalisation fused into the uint8 entry points (preprocess_core.h; 1 = rtpose)
     DevBuf<unsigned char> raw_stage;   // raw (un-resized) frames of b200pose_*crop* / b200pose_infer_raw_u8
 };
 
@@ -582,14 +583,14 @@ static int net_forward_impl(b200pose_net* net, const void* input, int in_u8, int
     if (mode == B200POSE_MODE_FP32) {
         if (in_u8) {   // parity mode: materialise rtpose_preprocess, then the fp32 path
             CU(net->f_u8.ensure(elems));
-            CU(u8hwc_to_f32nchw_launch(static_cast<const unsigned char*>(d_in), net->f_u8.p, n, H, W, st));
+            CU(u8hwc_to_f32nchw_launch(static_cast<const unsigned char*>(d_in), net->f_u8.p, n, H, W, net->preprocess, st));
             ++g_launches;
             rc = forward_fp32(net, net->f_u8.p, n, H, W, st);
         } else rc = forward_fp32(net, static_cast<const float*>(d_in), n, H, W, st);
-    } else rc = forward_bf16(net, d_in, in_u8, n, H, W, st, mode == B200POSE_MODE_BF16X3);
+    } else rc = forward_bf16(net, d_in, in_u8 ? net->preprocess : 0, n, H, W, st, mode == B200POSE_MODE_BF16X3);
     if (rc) return rc;
     net->last_in = d_in;
-    net->last_in_u8 = (mode == B200POSE_MODE_FP32) ? 0 : in_u8;
+    net->last_in_u8 = (mode == B200POSE_MODE_FP32) ? 0 : (in_u8 ? net->preprocess : 0);
     net->pn = n; net->pH = H; net->pW = W;
     if (outputs) {
         const size_t px8 = (size_t)n * (H / 8) * (W / 8);
@@ -612,6 +613,13 @@ int b200pose_net_forward_u8(b200pose_net* net, const unsigned char* images, int 
                             int mode, float* const* outputs, int outputs_on_device, void* cuda_stream) {
     return net_forward_impl(net, images, 1, input_on_device, n, H, W, mode, outputs, outputs_on_device,
                             reinterpret_cast<cudaStream_t>(cuda_stream), true);
+}
+
+int b200pose_net_set_preprocess(b200pose_net* net, int preprocess) {
+    if (!net) return fail("null net");
+    if (preprocess < 1 || preprocess > 4) return fail("preprocess must be 1 (rtpose), 2 (vgg), 3 (inception) or 4 (ssd)");
+    net->preprocess = preprocess;
+    return 0;
 }
 
 int b200pose_net_profile(b200pose_net* net, float* ms, double* flops, int cap, void* cuda_stream) {

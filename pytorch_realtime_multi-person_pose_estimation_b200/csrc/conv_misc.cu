@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "conv_misc.cuh"
+#include "preprocess_core.h"
 
 namespace b2p {
 
@@ -21,13 +22,15 @@ namespace {
 constexpr int kF_TW = 64, kF_TH = 4;        // output tile per block: 64 x 4 pixels, 2 pixels per thread
 constexpr int kF_Threads = 128;
 
-// kU8 = true: `in` is uint8 HWC BGR [N,H,W,3] and rtpose_preprocess (x/256 - 0.5, HWC -> CHW;
-// /root/reference/lib/datasets/preprocessing.py:16-21) is fused into the tile load.
-template <bool kU8>
+// kIn = 0: `in` is fp32 NCHW (already normalised).  kIn = kPreRtpose / kPreVgg / kPreInception / kPreSsd: `in` is uint8 HWC
+// BGR [N,H,W,3] and that normalisation (/root/reference/lib/datasets/preprocessing.py, restated in preprocess_core.h;
+// rtpose: x/256 - 0.5, HWC -> CHW) is fused into the tile load.
+template <int kIn>
 __global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const void* __restrict__ in_v, const float* __restrict__ wgt,
                                                                 const float* __restrict__ bias,
                                                                 __nv_bfloat16* __restrict__ out,
                                                                 __nv_bfloat16* __restrict__ out_lo, int H, int W) {
+    constexpr bool kU8 = kIn != 0;
     __shared__ float s_in[3][kF_TH + 2][kF_TW + 2];
     __shared__ __align__(16) float s_w[27][64];
     __shared__ float s_b[64];
@@ -56,8 +59,9 @@ __global__ void __launch_bounds__(kF_Threads) conv_first_kernel(const void* __re
         float v = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
             if (kU8) {
-                const unsigned char u = static_cast<const unsigned char*>(in_v)[(((size_t)n * H + gy) * W + gx) * 3 + c];
-                v = __fadd_rn(__fdiv_rn((float)u, 256.f), -0.5f);
+                const unsigned char u =
+                    static_cast<const unsigned char*>(in_v)[(((size_t)n * H + gy) * W + gx) * 3 + pre_src_channel(kIn, c)];
+                v = pre_value(kIn, u, c);
             } else {
                 v = static_cast<const float*>(in_v)[(((size_t)n * 3 + c) * H + gy) * W + gx];
             }
@@ -234,13 +238,20 @@ __global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ in, float* __r
 cudaError_t conv_first_launch(const void* in, int in_is_u8_hwc, const float* w_oihw, const float* bias,
                               __nv_bfloat16* out_nhwc, __nv_bfloat16* out_lo, int N, int H, int W, cudaStream_t s) {
     dim3 grid((W + kF_TW - 1) / kF_TW, (H + kF_TH - 1) / kF_TH, N);
-    if (in_is_u8_hwc) conv_first_kernel<true><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W);
-    else conv_first_kernel<false><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W);
+    switch (in_is_u8_hwc) {
+        case kPreNone: conv_first_kernel<kPreNone><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W); break;
+        case kPreRtpose: conv_first_kernel<kPreRtpose><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W); break;
+        case kPreVgg: conv_first_kernel<kPreVgg><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W); break;
+        case kPreInception: conv_first_kernel<kPreInception><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W); break;
+        case kPreSsd: conv_first_kernel<kPreSsd><<<grid, kF_Threads, 0, s>>>(in, w_oihw, bias, out_nhwc, out_lo, H, W); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
 namespace {
-__global__ void u8hwc_to_f32nchw_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, int N, int H, int W) {
+__global__ void u8hwc_to_f32nchw_kernel(const unsigned char* __restrict__ in, float* __restrict__ out, int N, int H, int W,
+                                        int mode) {
     const size_t total = (size_t)N * 3 * H * W;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int x = i % W;
@@ -249,15 +260,16 @@ __global__ void u8hwc_to_f32nchw_kernel(const unsigned char* __restrict__ in, fl
         t /= H;
         const int c = t % 3;
         const int n = t / 3;
-        out[i] = __fadd_rn(__fdiv_rn((float)in[(((size_t)n * H + y) * W + x) * 3 + c], 256.f), -0.5f);
+        out[i] = pre_value(mode, in[(((size_t)n * H + y) * W + x) * 3 + pre_src_channel(mode, c)], c);
     }
 }
 }  // namespace
 
-cudaError_t u8hwc_to_f32nchw_launch(const unsigned char* in, float* out, int N, int H, int W, cudaStream_t s) {
+cudaError_t u8hwc_to_f32nchw_launch(const unsigned char* in, float* out, int N, int H, int W, int mode, cudaStream_t s) {
+    if (mode < kPreRtpose || mode > kPreSsd) return cudaErrorInvalidValue;
     const size_t total = (size_t)N * 3 * H * W;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    u8hwc_to_f32nchw_kernel<<<blocks, 256, 0, s>>>(in, out, N, H, W);
+    u8hwc_to_f32nchw_kernel<<<blocks, 256, 0, s>>>(in, out, N, H, W, mode);
     return cudaGetLastError();
 }
 

@@ -16,11 +16,12 @@ struct ConvF32Args {
     int n_img, H, W, cin, cout, ks, relu;
 };
 
-// in: fp32 NCHW [N,3,H,W], or (in_is_u8_hwc) uint8 HWC BGR [N,H,W,3] with rtpose_preprocess fused into the load
+// in: fp32 NCHW [N,3,H,W] (in_is_u8_hwc = 0), or uint8 HWC BGR [N,H,W,3] with the normalisation `in_is_u8_hwc`
+// (preprocess_core.h: 1 rtpose, 2 vgg, 3 inception, 4 ssd) fused into the load
 cudaError_t conv_first_launch(const void* in, int in_is_u8_hwc, const float* w_oihw, const float* bias,
                               __nv_bfloat16* out_nhwc, __nv_bfloat16* out_lo /*residual plane or null*/, int N, int H,
                               int W, cudaStream_t s);
-cudaError_t u8hwc_to_f32nchw_launch(const unsigned char* in, float* out, int N, int H, int W, cudaStream_t s);
+cudaError_t u8hwc_to_f32nchw_launch(const unsigned char* in, float* out, int N, int H, int W, int mode, cudaStream_t s);
 cudaError_t conv_f32_launch(const ConvF32Args& a, cudaStream_t s);
 cudaError_t maxpool_f32_launch(const float* in, float* out, int N, int H, int W, int C, cudaStream_t s);
 cudaError_t nchw_to_nhwc_f32_launch(const float* in, float* out, int N, int C, int H, int W, int out_cstride,

@@ -28,6 +28,13 @@ class NativeNet:
             nat.check(L.b200pose_net_set_tensor(self._h, i, a.ctypes.data, a.size), "set_tensor(%d)" % i)
         nat.check(L.b200pose_net_finalize(self._h), "b200pose_net_finalize")
 
+    def set_preprocess(self, name):
+        """Normalisation fused into the uint8 entry points: 'rtpose' (default), 'vgg', 'inception' or 'ssd'
+        (lib/datasets/preprocessing.py; get_outputs' `preprocess` argument)."""
+        if name not in nat.PREPROCESS:
+            raise nat.B200PoseError("unknown preprocess %r (expected one of %s)" % (name, sorted(nat.PREPROCESS)))
+        nat.check(nat.lib().b200pose_net_set_preprocess(self._h, nat.PREPROCESS[name]), "b200pose_net_set_preprocess")
+
     def forward_ptr(self, in_ptr, in_on_device, n, H, W, mode, out_ptrs, out_on_device, stream):
         arr = (ctypes.c_void_p * 12)(*[ctypes.c_void_p(p) if p else None for p in out_ptrs])
         nat.check(nat.lib().b200pose_net_forward(self._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H, W, mode,

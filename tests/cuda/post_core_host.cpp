@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/post_core.h"
+#include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/preprocess_core.h"
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/resize_core.h"
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/tta_core.h"
 
@@ -184,5 +185,15 @@ extern "C" int core_resize_cubic(const float* src, int sh, int sw, int C, float*
             for (int c = 0; c < C; ++c) out[((long)y * dw + x) * C + c] = rs_cubic_at(src + c, (long)sw * C, C, cx, cy);
         }
     }
+    return 0;
+}
+
+// image normalisation with the exact functions conv_first_kernel calls (csrc/preprocess_core.h): uint8 HWC BGR [h,w,3]
+// -> float32 CHW [3,h,w]; mode 1 rtpose, 2 vgg, 3 inception, 4 ssd.
+extern "C" int core_preprocess(int mode, const unsigned char* img, int h, int w, float* out) {
+    for (int c = 0; c < 3; ++c)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+                out[((long)c * h + y) * w + x] = pre_value(mode, img[((long)y * w + x) * 3 + pre_src_channel(mode, c)], c);
     return 0;
 }

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/b200pose.h"
+#include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/preprocess_core.h"
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/resize_core.h"
 #include "../../pytorch_realtime_multi-person_pose_estimation_b200/csrc/tta_core.h"
 
@@ -131,6 +132,39 @@ static int raw_section(b200pose_net* net, b200pose_post* post) {
     ok = same(want, got);
     printf("%s  b200pose_infer_raw_u8(flip) == mirror raw + host crop + forward x2 + merge + post\n", ok ? "PASS" : "FAIL");
     failures += !ok;
+    return failures;
+}
+
+// vgg / inception / ssd normalisation fused into conv1_1 == the same normalisation on the host (shared core) + the fp32
+// entry point, bit for bit (not yet run on hardware in round 1: part of the "multiscale" group of sections)
+static int preprocess_section(b200pose_net* net) {
+    const int n = 2, H = 64, W = 72, h = H / 8, w = W / 8;
+    std::vector<unsigned char> fr((size_t)n * H * W * 3);
+    for (auto& b : fr) b = (unsigned char)(rnd() & 255);
+    int failures = 0;
+    const char* names[5] = {"", "rtpose", "vgg", "inception", "ssd"};
+    for (int pm = 4; pm >= 1; --pm) {      // ends on rtpose, the default of every other section
+        if (b200pose_net_set_preprocess(net, pm)) { printf("FAIL set_preprocess %d\n", pm); return failures + 1; }
+        std::vector<float> x((size_t)n * 3 * H * W);
+        for (int i = 0; i < n; ++i)
+            for (int c = 0; c < 3; ++c)
+                for (int y = 0; y < H; ++y)
+                    for (int xx = 0; xx < W; ++xx)
+                        x[(((size_t)i * 3 + c) * H + y) * W + xx] =
+                            b2p::pre_value(pm, fr[(((size_t)i * H + y) * W + xx) * 3 + b2p::pre_src_channel(pm, c)], c);
+        for (int mode = 0; mode < 2; ++mode) {
+            std::vector<float> pa((size_t)n * 38 * h * w), ha((size_t)n * 19 * h * w), pb(pa.size()), hb(ha.size());
+            float* outs[12] = {nullptr};
+            outs[10] = pa.data(); outs[11] = ha.data();
+            CHECK(b200pose_net_forward_u8(net, fr.data(), 0, n, H, W, mode, outs, 0, nullptr));
+            outs[10] = pb.data(); outs[11] = hb.data();
+            CHECK(b200pose_net_forward(net, x.data(), 0, n, H, W, mode, outs, 0, nullptr));
+            const bool ok = !memcmp(pa.data(), pb.data(), pa.size() * 4) && !memcmp(ha.data(), hb.data(), ha.size() * 4);
+            printf("%s  preprocess %-9s fused into conv1_1 == host normalisation + fp32 entry [%s]\n", ok ? "PASS" : "FAIL",
+                   names[pm], mode ? "fp32" : "bf16");
+            failures += !ok;
+        }
+    }
     return failures;
 }
 
@@ -318,6 +352,7 @@ int main(int argc, char** argv) {
     }
     failures += raw_section(net, post);
     if (with_multiscale) {
+        failures += preprocess_section(net);
         failures += multiscale_section(net, post, 0);
         failures += multiscale_section(net, post, 1);
     }

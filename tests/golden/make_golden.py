@@ -14,7 +14,7 @@ import os
 import sys
 import types
 
-ARGS = sys.argv[1:]     # optional: "crop" / "eval" regenerate only those small fixtures
+ARGS = sys.argv[1:]     # optional: "crop" / "eval" / "pre" regenerate only those small fixtures
 
 import numpy as np
 
@@ -132,14 +132,30 @@ def make_eval(ref_eval):
     print("append_result", len(outputs), "records")
 
 
+def make_preprocess():
+    """The four image normalisations of the reference (lib/datasets/preprocessing.py) on an image that holds every
+    uint8 value in every channel."""
+    from lib.datasets import preprocessing as ref_pre
+    img = np.zeros((16, 16, 3), np.uint8)
+    img[:, :, 0] = np.arange(256).reshape(16, 16)
+    img[:, :, 1] = np.arange(256)[::-1].reshape(16, 16)
+    img[:, :, 2] = (np.arange(256) * 7 % 256).reshape(16, 16)
+    np.savez_compressed(os.path.join(OUT, "preprocess.npz"), img=img, rtpose=ref_pre.rtpose_preprocess(img.copy()),
+                        vgg=ref_pre.vgg_preprocess(img.copy()), inception=ref_pre.inception_preprocess(img.copy()),
+                        ssd=ref_pre.ssd_preprocess(img.copy()))
+    print("preprocess fixture written")
+
+
 def main():
     import torch
     get_model, ref_p2p, ref_eval, cfg = import_reference()
+    if not ARGS or "pre" in ARGS:
+        make_preprocess()
     if not ARGS or "crop" in ARGS:
         make_crop()
     if not ARGS or "eval" in ARGS:
         make_eval(ref_eval)
-    if ARGS and set(ARGS) <= {"crop", "eval"}:
+    if ARGS and set(ARGS) <= {"crop", "eval", "pre"}:
         return
     torch.manual_seed(0)
 

@@ -207,3 +207,32 @@ def test_multiscale_flip_averaging_matches_composed_oracle(built, he_sd):
         assert_humans_equal(got[i], want, score_tol=0.0)
         total += len(want)
     assert total > 0
+
+
+@PENDING
+def test_every_preprocess_mode_fused_into_conv1_1(built, he_sd):
+    """b200pose_net_set_preprocess: the uint8 entry point with 'vgg' / 'inception' / 'ssd' / 'rtpose' fused into the first
+    convolution gives the very same maps as the numpy function on the host + the fp32-input entry point (bf16 and fp32
+    modes)."""
+    eng = pkg_module("engine")
+    nat = pkg_module("_native")
+    pre = pkg_module("lib.datasets.preprocessing")
+    net = eng.NativeNet(0)
+    net.load_state_dict_arrays([v.numpy() for v in he_sd.values()])
+    img = np.random.RandomState(17).randint(0, 256, (2, 64, 72, 3)).astype(np.uint8)
+    xd = torch.from_numpy(img).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, fn in (("vgg", pre.vgg_preprocess), ("inception", pre.inception_preprocess), ("ssd", pre.ssd_preprocess),
+                     ("rtpose", pre.rtpose_preprocess)):
+        net.set_preprocess(name)
+        xf = torch.from_numpy(np.stack([fn(i) for i in img])).cuda().contiguous()
+        for mode in ("bf16", "fp32"):
+            a = [torch.empty((2, 38 if i % 2 == 0 else 19, 8, 9), device="cuda") for i in range(12)]
+            b = [torch.empty_like(t) for t in a]
+            net.forward_u8_ptr(xd.data_ptr(), True, 2, 64, 72, nat.MODES[mode], [o.data_ptr() for o in a], True, stream)
+            net.forward_ptr(xf.data_ptr(), True, 2, 64, 72, nat.MODES[mode], [o.data_ptr() for o in b], True, stream)
+            torch.cuda.synchronize()
+            for u, v in zip(a, b):
+                assert torch.equal(u, v), (name, mode)
+    with pytest.raises(nat.B200PoseError):
+        net.set_preprocess("caffe")

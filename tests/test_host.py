@@ -107,6 +107,24 @@ def test_preprocess_and_flip_match_oracle():
     np.testing.assert_array_equal(ah, bh)
 
 
+def test_preprocess_device_core_on_host_matches_reference_golden(built):
+    """csrc/preprocess_core.h (what conv_first_kernel applies while loading uint8 frames) compiled for the host, the
+    product's numpy functions and the reference's own functions (golden) agree bit for bit on every uint8 value, for
+    all four `preprocess` modes of get_outputs."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "build", "libpostcore_host.so"))
+    lib.core_preprocess.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    pre = pkg_module("lib.datasets.preprocessing")
+    nat = pkg_module("_native")
+    f = golden("preprocess")
+    img = np.ascontiguousarray(f["img"])
+    for name, fn in (("rtpose", pre.rtpose_preprocess), ("vgg", pre.vgg_preprocess), ("inception", pre.inception_preprocess),
+                     ("ssd", pre.ssd_preprocess)):
+        out = np.empty((3,) + img.shape[:2], np.float32)
+        lib.core_preprocess(nat.PREPROCESS[name], img.ctypes.data, img.shape[0], img.shape[1], out.ctypes.data)
+        np.testing.assert_array_equal(out, f[name])
+        np.testing.assert_array_equal(fn(img.copy()), f[name])
+
+
 def _flip_inputs():
     """The seeded inputs tests/golden/make_golden.py fed to the reference's handle_paf_and_heat."""
     return [np.random.RandomState(sd).rand(6, 5, c).astype(np.float32) for sd, c in ((1, 19), (2, 19), (3, 38), (4, 38))]
