@@ -105,6 +105,10 @@ int b200pose_post_sync(b200pose_post* post);
 /* Diagnostics: out[0..2] = max SM cycles of the limbs kernel phases (scoring, exact sort, greedy) over all blocks since
  * the last reset, out[3] = max candidates of a limb, out[4] = total candidates. */
 int b200pose_post_debug(b200pose_post* post, unsigned long long* out, int n, int reset);
+/* OR of the status words of every image of every run since the last reset (sticky accumulator kept on the device):
+ * with runs in flight a caller reads only some results back; this proves that no run at all overflowed a capacity
+ * (the reference's std::vectors grow without bound, pafprocess.cpp:24-44, so an overflow is a divergence).  < 0 on error. */
+int b200pose_post_status_accum(b200pose_post* post, int reset);
 int b200pose_post_num_humans(b200pose_post* post, int img);             /* < 0 on error */
 int b200pose_post_status(b200pose_post* post, int img);                 /* status bits of the last run */
 int b200pose_post_get_humans(b200pose_post* post, int img, float* out, int max_humans);   /* returns count */

@@ -139,9 +139,9 @@ struct b200pose_net {
     std::vector<ConvTcArgs> plan;
     std::vector<double> plan_flops;   // algorithmic FLOPs per launch of `plan`
     bool plan_split = false;          // the plan was built for the split-precision (bf16x3) mode
-    // EXPERIMENT (off unless B200POSE_PLAN_CACHE=1 when the net is created): keep the plans of other (n, H, W, mode)
-    // keys so that alternating shapes (multi-scale, mixed frame sizes) do not re-encode 51 tensor maps and synchronise
-    // the stream.  An entry is valid while the activation buffers it points into have not been reallocated.
+    // Plans of other (n, H, W, mode) keys are kept, so that alternating shapes (multi-scale, mixed frame sizes) do not
+    // re-encode 51 tensor maps and synchronise the stream.  An entry is valid while the activation buffers it points
+    // into have not been reallocated.  B200POSE_PLAN_CACHE=0 (read when the net is created) turns it off.
     struct PlanEntry {
         int n, H, W, mode;
         bool split;
@@ -149,7 +149,7 @@ struct b200pose_net {
         std::vector<double> flops;
         std::vector<const void*> buffers;
     };
-    bool plan_cache_on = false;
+    bool plan_cache_on = true;
     int kn = 0, kH = 0, kW = 0, kmode = -1;      // key of the plan currently held in `plan`
     std::vector<PlanEntry> plan_cache;
     DevBuf<__nv_bfloat16> t1, t2, t3, t4, t5a, t5b, t6, t7, t8, t9, cat, bra, brb, br512;
@@ -176,7 +176,6 @@ struct b200pose_post {
     // of two slots selected by the run's parity, so the host can fetch run i while run i+1 is in flight.
     cudaStream_t s2 = nullptr;
     cudaEvent_t ev_limbs = nullptr, ev_asm = nullptr, ev_fetch[2] = {nullptr, nullptr};
-    bool have_asm = false;
     long runs = 0;                  // runs submitted so far; ticket of the latest = runs - 1
     int slot_n[2] = {0, 0};
     int* hp_nh[2] = {nullptr, nullptr};
@@ -188,9 +187,12 @@ struct b200pose_post {
     std::vector<float> h_px_s;
     std::vector<int> h_px, h_py;
     int hw_h = 0, hw_w = 0;
-    // EXPERIMENT (off unless B200POSE_POST_OVERLAP=1 when the object is created): peaks / limbs / assembly of run i all
-    // run on the second stream from a private copy of the maps, so they can overlap the convolutions of run i+1.
-    bool overlap = false;
+    // Peaks / limbs / assembly of run i all run on the second stream from a private copy of the maps (15 MB at batch 32),
+    // so that the caller's stream is free for the convolutions of run i+1: the small kernels (peaks, assembly) co-reside
+    // with the conv CTAs and the limbs blocks fill the SMs the conv launches leave idle in their last wave
+    // (measured on B200, batch 32: 14.23 -> 13.52 ms per step device-resident, 14.26 -> 13.15 end to end;
+    // profiles/r02_variants.txt).  B200POSE_POST_OVERLAP=0 keeps everything on the caller's stream.
+    bool overlap = true;
     DevBuf<float> ov_maps[2];                       // [heat | paf] copies, slot = run parity
     cudaEvent_t ev_maps = nullptr, ev_ld[2] = {nullptr, nullptr};   // maps copied (st) / limbs done with a slot (s2)
     bool have_ld[2] = {false, false};
@@ -481,7 +483,7 @@ int b200pose_net_create(b200pose_net** out, int cuda_device) {
     net->host_b.resize(kNumConvs);
     net->have.assign(B200POSE_NUM_TENSORS, false);
     const char* pc = getenv("B200POSE_PLAN_CACHE");
-    net->plan_cache_on = pc && pc[0] == '1';
+    net->plan_cache_on = !(pc && pc[0] == '0');
     *out = net;
     return 0;
 }
@@ -685,7 +687,7 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
     }
     CU(cudaEventCreateWithFlags(&p->ev_maps, cudaEventDisableTiming));
     const char* ov = getenv("B200POSE_POST_OVERLAP");
-    p->overlap = ov && ov[0] == '1';
+    p->overlap = !(ov && ov[0] == '0');
     *out = p;
     return 0;
 }
@@ -721,7 +723,6 @@ static int enqueue_assemble_and_fetch(b200pose_post* p, int n, cudaStream_t st) 
     if (e != cudaSuccess) return fail("post_assemble: %s", cudaGetErrorString(e));
     ++g_launches;
     CU(cudaEventRecord(p->ev_asm, p->s2));
-    p->have_asm = true;
     const int b = (int)(p->runs & 1);
     const PostBuffers& pb = p->pb;
     CU(cudaMemcpyAsync(p->hp_nh[b], pb.n_humans, n * sizeof(int), cudaMemcpyDeviceToHost, p->s2));
@@ -755,8 +756,10 @@ static int post_run_dev(b200pose_post* p, const float* d_heat, const float* d_pa
         d_paf = p->ov_maps[slot].p + eh;
         ps = p->s2;
     }
-    // the previous run's assembly (second stream) still reads the peak / connection buffers this run overwrites
-    if (p->have_asm) CU(cudaStreamWaitEvent(ps, p->ev_asm, 0));
+    // the previous run's assembly (second stream) still reads the peak / connection buffers this run overwrites, and
+    // its D2H copies of status / counts (enqueued after the assembly) must not race with this run's memset + peaks:
+    // wait for the event recorded after those copies
+    if (p->runs > 0) CU(cudaStreamWaitEvent(ps, p->ev_fetch[(p->runs - 1) & 1], 0));
     cudaError_t e;
     if (layout == 0) {
         e = post_peaks(p->pb, n, d_heat, (long)19 * h * w, (long)h * w, w, 1, h, w, thresh, ps);
@@ -809,6 +812,20 @@ int b200pose_post_sync(b200pose_post* p) {
     if (!p) return fail("null post");
     if (p->runs == 0) return fail("no run submitted");
     return b200pose_post_select(p, p->runs - 1);
+}
+
+int b200pose_post_status_accum(b200pose_post* p, int reset) {
+    // OR of the status words of every image of every run since the last reset: lets a caller that keeps runs in flight
+    // (and only reads some of them back) prove that NO run overflowed a capacity
+    if (!p) return -1;
+    if (cudaSetDevice(p->device) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(p->s2) != cudaSuccess) return -1;
+    std::vector<int> h(p->pb.batch_cap);
+    if (cudaMemcpy(h.data(), p->pb.status_acc, h.size() * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset && cudaMemset(p->pb.status_acc, 0, h.size() * sizeof(int)) != cudaSuccess) return -1;
+    int acc = 0;
+    for (int v : h) acc |= v;
+    return acc;
 }
 
 int b200pose_post_debug(b200pose_post* p, unsigned long long* out, int n, int reset) {
@@ -1172,6 +1189,7 @@ int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, fl
     }
     const PostBuffers& pb = p->pb;
     cudaStream_t st = nullptr;
+    if (p->runs > 0) CU(cudaStreamWaitEvent(st, p->ev_fetch[(p->runs - 1) & 1], 0));   // previous call's second-stream work
     CU(cudaMemsetAsync(pb.status, 0, sizeof(int), st));
     CU(cudaMemcpyAsync(pb.counts, counts.data(), 18 * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(pb.peak_x, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice, st));
@@ -1179,7 +1197,6 @@ int process_paf(int p1, int p2, int p3, float* peaks, int h1, int h2, int h3, fl
     CU(cudaMemcpyAsync(pb.peak_s, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice, st));
     CU(p->d_paf.ensure((size_t)f1 * f2 * f3));
     CU(cudaMemcpyAsync(p->d_paf.p, pafmap, (size_t)f1 * f2 * f3 * 4, cudaMemcpyHostToDevice, st));
-    if (p->have_asm) CU(cudaStreamWaitEvent(st, p->ev_asm, 0));
     cudaError_t e = post_limbs(pb, 1, p->d_paf.p, 0, 1, (long)f2 * f3, f3, 0, h1, f2, f1, st);
     if (e != cudaSuccess) return fail("post_limbs: %s", cudaGetErrorString(e));
     ++g_launches;

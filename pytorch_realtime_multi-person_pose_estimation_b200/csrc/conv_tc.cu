@@ -21,6 +21,7 @@
 #include <cstdio>
 
 #include "conv_tc.cuh"
+#include "host_util.h"
 #include "ptx.cuh"
 
 namespace b2p {
@@ -380,12 +381,10 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
 }
 
 cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvTcSmemBytes);
+    static DynSmemOptIn optin;      // per device: a second net on another GPU of the same process needs its own opt-in
+    {
+        cudaError_t e = optin.ensure(conv_tc_kernel, kConvTcSmemBytes);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     if (a.pool && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
     const int tiles_x = (a.W + kTileW - 1) / kTileW;

@@ -16,7 +16,9 @@ constexpr int kMaxKs = 7;
 constexpr int kPatchBytes = kPatchPitch * (kTileH + kMaxKs - 1) * 128;  // 67,584 B per 64-channel block
 constexpr int kBStageBytes = 128 * 128;                                 // up to N=128 rows of 64 bf16
 #ifndef B2P_CONV_B_STAGES
-#define B2P_CONV_B_STAGES 5      // weight (B operand) pipeline depth; tools/variants.py builds the library with other values
+#define B2P_CONV_B_STAGES 3      // weight (B operand) pipeline depth: 3, 4 and 5 stages measure the same on B200 (2245 / 2246 /
+                                 // 2249 frames/s, profiles/r02_variants.txt); 3 leaves 42 KB of the SM's shared memory to
+                                 // the post-processing kernels of the previous batch that run next to the convolutions
 #endif
 constexpr int kNumBStages = B2P_CONV_B_STAGES;
 constexpr int kNumPatchStages = 2;

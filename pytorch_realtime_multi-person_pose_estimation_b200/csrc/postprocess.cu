@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "host_util.h"
 #include "postprocess.cuh"
 
 namespace b2p {
@@ -600,23 +601,9 @@ __device__ int greedy_segmented(const uint64_t* keys, int n, int nb, uint32_t* u
     return *s_nc;
 }
 
-// B2P_LIMBS_PERSISTENT (tools/variants.py, co-residency study): instead of one block per (image, limb) the grid is a
-// fixed number of blocks (about one per SM) that pull (image, limb-rank) items from an atomic counter (pb.dbg[15], zeroed
-// by the host) in the same longest-job-first order.  At most one such block then sits next to a conv CTA on an SM.
-#ifndef B2P_LIMBS_PERSISTENT
-#define B2P_LIMBS_PERSISTENT 0
-#endif
-#if B2P_LIMBS_PERSISTENT
-#define B2P_ITEM_DONE continue
-#else
 #define B2P_ITEM_DONE return
-#endif
 __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, PafView paf0, long p_img, int h_up, int lw,
-                                                             int lh, int paf_in_smem
-#if B2P_LIMBS_PERSISTENT
-                                                             , int batch
-#endif
-                                                             ) {
+                                                             int lh, int paf_in_smem) {
     // dynamic smem: [kSmemRange keys][2 x (kSmemRange + 2) int32 partition scratch][optional 2 PAF planes]
     extern __shared__ unsigned long long sm_keys[];
     int32_t* sm_scr = reinterpret_cast<int32_t*>(sm_keys + kSmemRange);
@@ -627,17 +614,7 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
     // Longest-job-first: grid = (image, rank); block `rank` of an image takes the limb with the rank-th largest number
     // of (a, b) pairs, so across the whole grid the heavy limbs are scheduled before the light ones (shorter tail).
     const int tid = threadIdx.x;
-#if B2P_LIMBS_PERSISTENT
-    __shared__ int s_item;
-    for (;;) {
-    __syncthreads();                                  // the previous item's shared state is dead
-    if (tid == 0) s_item = (int)atomicAdd(pb.dbg + 15, 1ull);
-    __syncthreads();
-    if (s_item >= batch * kNumLimb) return;
-    const int img = s_item % batch, rank_y = s_item / batch;
-#else
     const int img = blockIdx.x, rank_y = blockIdx.y;
-#endif
     int limb = rank_y;
     {
         int my_pairs[kNumLimb];
@@ -770,9 +747,6 @@ __global__ void __launch_bounds__(kLimbThreads) limbs_kernel(PostBuffers pb, Paf
             }
         }
     }
-#if B2P_LIMBS_PERSISTENT
-    }
-#endif
 }
 
 // ------------------------------------------------------------------ assembly
@@ -863,7 +837,9 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(PostBuffers pb) {
             }
         if (as.overflow) st |= 4;
         if (as.degraded) st |= 16;
-        if (st) atomicOr(&pb.status[img], st);
+        // this block is the last writer of the image's status word: fold it into the sticky accumulator as well
+        const int st_all = (st ? atomicOr(&pb.status[img], st) : pb.status[img]) | st;
+        if (st_all) atomicOr(&pb.status_acc[img], st_all);
         s_nh = nh;
         s_nrows = as.nrows;
         pb.n_humans[img] = nh;
@@ -923,6 +899,8 @@ cudaError_t post_alloc(PostBuffers& pb, int batch_cap, int peak_cap, int human_c
     B2P_TRY(cudaMalloc(&pb.n_humans, B * sizeof(int)));
     B2P_TRY(cudaMalloc(&pb.humans, B * human_cap * kHumanFloats * sizeof(float)));
     B2P_TRY(cudaMalloc(&pb.status, B * sizeof(int)));
+    B2P_TRY(cudaMalloc(&pb.status_acc, B * sizeof(int)));
+    B2P_TRY(cudaMemset(pb.status_acc, 0, B * sizeof(int)));
     B2P_TRY(cudaMalloc(&pb.dbg, 16 * sizeof(unsigned long long)));
     B2P_TRY(cudaMemset(pb.dbg, 0, 16 * sizeof(unsigned long long)));
     B2P_TRY(cudaMemset(pb.status, 0, B * sizeof(int)));
@@ -933,7 +911,7 @@ cudaError_t post_alloc(PostBuffers& pb, int batch_cap, int peak_cap, int human_c
 void post_free(PostBuffers& pb) {
     void* ptrs[] = {pb.counts, pb.peak_x, pb.peak_y, pb.peak_s,  pb.conn_cnt, pb.conn_a,      pb.conn_b,
                     pb.conn_s, pb.rows,   pb.alive,  pb.lists,   pb.list_n,   pb.id_score,    pb.id_xy,
-                    pb.pool,   pb.pool_cursor, pb.n_humans, pb.humans, pb.status, pb.dbg};
+                    pb.pool,   pb.pool_cursor, pb.n_humans, pb.humans, pb.status, pb.status_acc, pb.dbg};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     memset(&pb, 0, sizeof(pb));
@@ -944,11 +922,8 @@ cudaError_t post_peaks(const PostBuffers& pb, int batch, const float* heat, long
     if (batch > pb.batch_cap) return cudaErrorInvalidValue;
     const size_t smem = ((size_t)h * w + (kPeakThreads / 32) * 5 * kHorStride) * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        B2P_TRY(cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    static DynSmemOptIn optin;
+    B2P_TRY(optin.ensure(peaks_kernel, smem));
     B2P_TRY(cudaMemsetAsync(pb.status, 0, batch * sizeof(int), s));
     peaks_kernel<<<dim3(kNumPart, batch), kPeakThreads, smem, s>>>(pb, heat, h_img, h_ch, h_y, h_x, h, w, thresh);
     return cudaGetLastError();
@@ -962,24 +937,13 @@ cudaError_t post_limbs(const PostBuffers& pb, int batch, const float* paf, long 
     if (pb.cand_smem_cap != kSmemRange) return cudaErrorInvalidValue;
     size_t smem = kSmemRange * sizeof(unsigned long long) + 2 * (kSmemRange + 2) * sizeof(int32_t);
     int in_smem = 0;
-    // EXPERIMENT switch (round-2 co-residency study): keep the PAF planes in global memory / L2 to shrink the footprint
-    static const bool paf_global = [] { const char* v = getenv("B200POSE_LIMBS_PAF_GLOBAL"); return v && v[0] == '1'; }();
-    if (!paf_global && shift == 3 && (size_t)2 * lw * lh * sizeof(float) <= 96 * 1024) {
+    if (shift == 3 && (size_t)2 * lw * lh * sizeof(float) <= 96 * 1024) {
         in_smem = 1;
         smem += (size_t)2 * lw * lh * sizeof(float);
     }
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-        B2P_TRY(cudaFuncSetAttribute(limbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
-#if B2P_LIMBS_PERSISTENT
-    static const int grid = [] { const char* v = getenv("B200POSE_LIMBS_GRID"); const int g = v ? atoi(v) : 148; return g > 0 ? g : 148; }();
-    B2P_TRY(cudaMemsetAsync(pb.dbg + 15, 0, sizeof(unsigned long long), s));
-    limbs_kernel<<<grid < batch * kNumLimb ? grid : batch * kNumLimb, kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem, batch);
-#else
+    static DynSmemOptIn optin;
+    B2P_TRY(optin.ensure(limbs_kernel, smem));
     limbs_kernel<<<dim3(batch, kNumLimb), kLimbThreads, smem, s>>>(pb, pv, p_img, h_up, lw, lh, in_smem);
-#endif
     return cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ struct PostBuffers {
     int* n_humans;      // [B]
     float* humans;      // [B][human_cap][1 + 18*4]: score, then per part (x, y, peak score, cid or -1)
     unsigned long long* dbg;   // [16] diagnostics: max cycles per limbs_kernel phase, candidate counts
+    int* status_acc;    // [B] OR of `status` over every run since the last reset (b200pose_post_status_accum)
     int* status;        // [B] bit0 peak overflow, bit1 candidate pool overflow, bit2 row overflow, bit3 human overflow,
                         //     bit4 assembler used the slow scan, bit8.. number of limbs that needed the tie-exact sort
 };

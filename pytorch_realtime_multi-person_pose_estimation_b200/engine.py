@@ -122,6 +122,13 @@ class NativePost:
     def status(self, img):
         return int(nat.lib().b200pose_post_status(self._h, img))
 
+    def status_accum(self, reset=False):
+        """OR of the status bits of every image of every run since the last reset (waits for the second stream)."""
+        st = int(nat.lib().b200pose_post_status_accum(self._h, int(bool(reset))))
+        if st < 0:
+            nat.check(1, "b200pose_post_status_accum")
+        return st
+
     def check_status(self, n):
         for i in range(n):
             st = self.status(i)
@@ -189,20 +196,39 @@ class PoseEngine:
         self.post = NativePost(device_index, batch_cap, peak_cap, human_cap)
         self.mode = nat.MODES[mode]
         self.device_index = device_index
+        self._shapes = {}
+        self._last = None
+
+    def _remember(self, n, H, W):
+        """Shape of the run just submitted, kept per ticket (two runs may be in flight with different batch sizes or
+        frame shapes: fetch(ticket=i) must read run i with run i's n and normalise by run i's W / H)."""
+        t = self.post.last_ticket()
+        if self.__dict__.get("_shapes") is None:
+            self._shapes = {}
+        self._shapes[t] = (n, H, W)
+        for old in [k for k in self._shapes if k < t - 1]:
+            del self._shapes[old]
+        self._last = (n, H, W)
+        return t
+
+    def _shape_of(self, ticket):
+        if ticket is None:
+            return self._last
+        if ticket not in (self.__dict__.get("_shapes") or {}):
+            raise nat.B200PoseError("ticket %r is not one of the last two runs" % (ticket,))
+        return self._shapes[ticket]
 
     def infer_async(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
         nat.check(nat.lib().b200pose_infer(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H, W,
                                            self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)), "b200pose_infer")
-        self._last = (n, H, W)
-        return self.post.last_ticket()
+        return self._remember(n, H, W)
 
     def infer_async_u8(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
         """uint8 HWC BGR frames [n,H,W,3] (host pinned or device); preprocessing runs on the device."""
         nat.check(nat.lib().b200pose_infer_u8(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H,
                                               W, self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
                   "b200pose_infer_u8")
-        self._last = (n, H, W)
-        return self.post.last_ticket()
+        return self._remember(n, H, W)
 
     def infer_flip_async(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
         """Flip test-time averaging (fp32 NCHW input): frames + device-made mirrored copies as one 2n batch, maps merged
@@ -210,15 +236,13 @@ class PoseEngine:
         nat.check(nat.lib().b200pose_infer_flip(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n,
                                                 H, W, self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
                   "b200pose_infer_flip")
-        self._last = (n, H, W)
-        return self.post.last_ticket()
+        return self._remember(n, H, W)
 
     def infer_flip_async_u8(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
         nat.check(nat.lib().b200pose_infer_u8_flip(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device),
                                                    n, H, W, self.mode, ctypes.c_float(thresh), ctypes.c_void_p(stream)),
                   "b200pose_infer_u8_flip")
-        self._last = (n, H, W)
-        return self.post.last_ticket()
+        return self._remember(n, H, W)
 
     def infer_raw_async_u8(self, in_ptr, in_on_device, n, src_h, src_w, dest_size=368, factor=8, thresh=0.1, flip=False,
                            stream=0):
@@ -229,8 +253,7 @@ class PoseEngine:
                                                   ctypes.c_float(thresh), int(bool(flip)), ctypes.c_void_p(stream)),
                   "b200pose_infer_raw_u8")
         _, _, (ph, pw) = nat.crop_geometry(src_h, src_w, dest_size, factor)
-        self._last = (n, ph, pw)
-        return self.post.last_ticket()
+        return self._remember(n, ph, pw)
 
     def infer_raw_multiscale_async_u8(self, in_ptr, in_on_device, n, src_h, src_w, scales, base_size=368, factor=8,
                                       thresh=0.1, flip=False, stream=0):
@@ -245,8 +268,7 @@ class PoseEngine:
                                                              ctypes.c_void_p(stream)),
                   "b200pose_infer_raw_u8_multiscale")
         _, _, (ph, pw) = nat.crop_geometry(src_h, src_w, base_size, factor)
-        self._last = (n, ph, pw)
-        return self.post.last_ticket()
+        return self._remember(n, ph, pw)
 
     def infer_images(self, images, dest_size=368, factor=8, thresh=0.1, flip=False, scales=None):
         """images: a list of raw uint8 BGR frames of arbitrary (mixed) sizes, as cv2.imread returns them.  Frames are
@@ -275,7 +297,7 @@ class PoseEngine:
 
     def fetch(self, check=True, ticket=None):
         """Results of run `ticket` (default: the latest).  Up to two runs may be in flight: submit i+1, then fetch i."""
-        n, H, W = self._last
+        n, H, W = self._shape_of(ticket)
         if ticket is None:
             self.post.sync()
         else:
@@ -287,7 +309,7 @@ class PoseEngine:
     def fetch_arrays(self, check=True, ticket=None):
         """Like fetch() but without building Python objects: per image a float32 array [k, 73] with rows
         (score, 18 x (x, y, peak score, peak id | -1)), x / y in pixels of the (padded) network input."""
-        n, H, W = self._last
+        n, H, W = self._shape_of(ticket)
         if ticket is None:
             self.post.sync()
         else:

@@ -20,7 +20,20 @@ ORDER_COCO = [0, 15, 14, 17, 16, 5, 2, 6, 3, 7, 4, 11, 8, 12, 9, 13, 10]   # coc
 
 
 def get_outputs(img, model, preprocess):
-    """img: HWC uint8 BGR -> (paf [h,w,38] f32, heatmap [h,w,19] f32, im_scale)."""
+    """img: HWC uint8 BGR -> (paf [h,w,38] f32, heatmap [h,w,19] f32, im_scale).
+
+    With a model from this package's get_model() (bare, or wrapped in DataParallel as the demo does) the whole body
+    runs on the device: the raw frame is uploaded as bytes, crop_with_factor and the normalisation are kernels (both
+    bit-identical to the host functions the reference calls), and only the two final maps are copied back.  Any other
+    nn.Module takes the reference's own sequence below."""
+    core = getattr(model, "module", model)
+    if (hasattr(core, "maps_from_frame") and preprocess in ('rtpose', 'vgg', 'inception', 'ssd')
+            and isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
+            and cfg.MODEL.DOWNSAMPLE % 8 == 0):
+        paf_t, heat_t, im_scale = core.maps_from_frame(img, preprocess, cfg.DATASET.IMAGE_SIZE, cfg.MODEL.DOWNSAMPLE)
+        heatmap = heat_t.cpu().data.numpy().transpose(0, 2, 3, 1)[0]
+        paf = paf_t.cpu().data.numpy().transpose(0, 2, 3, 1)[0]
+        return paf, heatmap, im_scale
     im_croped, im_scale, _ = im_transform.crop_with_factor(img, cfg.DATASET.IMAGE_SIZE, factor=cfg.MODEL.DOWNSAMPLE,
                                                            is_ceil=True)
     if preprocess == 'rtpose':

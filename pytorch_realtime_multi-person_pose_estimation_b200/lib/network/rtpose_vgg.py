@@ -11,7 +11,7 @@ Precision: `model.precision = 'bf16'` (default; tcgen05 tensor cores, fp32 accum
 the environment variable B200POSE_MODE sets the default.
 """
 import os
-from collections import OrderedDict
+import threading
 
 import torch
 import torch.nn as nn
@@ -60,25 +60,93 @@ class rtpose_model(nn.Module):
             setattr(self, "model%d_2" % s, _make_branch(_stage_spec(s, 19)))
         self.precision = os.environ.get("B200POSE_MODE", "bf16")
         self._engines = {}     # device index -> (signature, NativeNet); shared by DataParallel replicas
+        self._lock = threading.Lock()
+        # DataParallel replicas are shallow copies with EMPTY `_parameters` (torch/nn/parallel/replicate.py): plain
+        # attributes like this box travel with the copy, so a replica finds the module that owns the weights.  (A list,
+        # not the module itself: nn.Module.__setattr__ would register it as a child of itself.)
+        self._master = [self]
         for m in self.modules():   # same init as rtpose_vgg.py:200-222
             if isinstance(m, nn.Conv2d):
                 nn.init.normal_(m.weight, std=0.01)
                 nn.init.constant_(m.bias, 0.0)
 
     def _signature(self):
-        ps = list(self.parameters())
-        return tuple((p.data_ptr(), p._version) for p in (ps[0], ps[len(ps) // 2], ps[-1]))
+        # every one of the 184 tensors: an in-place edit (or a load_state_dict) of ANY of them bumps its version
+        return tuple((p.data_ptr(), p._version) for p in self.state_dict(keep_vars=True).values())
 
     def _engine(self, device):
+        """The native net of `device`, (re)packed from the weights of the module that owns them.  Called on the master
+        or on a DataParallel replica (whose own parameters()/state_dict() are empty); replicas run in threads."""
+        master = self._master[0]
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        sig = self._signature()
-        cached = self._engines.get(idx)
-        if cached is None or cached[0] != sig:
-            net = cached[1] if cached is not None else NativeNet(idx)
-            arrays = [p.detach().to(torch.float32).cpu().contiguous().numpy() for p in self.state_dict().values()]
-            net.load_state_dict_arrays(arrays)
-            self._engines[idx] = (sig, net)
-        return self._engines[idx][1]
+        with master._lock:
+            sig = master._signature()
+            if len(sig) != nat.NUM_TENSORS:
+                raise nat.B200PoseError("rtpose_model: expected %d weight tensors, found %d" % (nat.NUM_TENSORS, len(sig)))
+            cached = master._engines.get(idx)
+            if cached is None or cached[0] != sig:
+                net = cached[1] if cached is not None else NativeNet(idx)
+                arrays = [p.detach().to(torch.float32).cpu().contiguous().numpy()
+                          for p in master.state_dict(keep_vars=True).values()]
+                net.load_state_dict_arrays(arrays)
+                master._engines[idx] = (sig, net)
+            return master._engines[idx][1]
+
+    def __deepcopy__(self, memo):
+        # the copy owns its own weights, engines and lock (a lock cannot be deep-copied)
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_engines", "_lock", "_master"):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.__dict__["_engines"] = {}
+        new.__dict__["_lock"] = threading.Lock()
+        new.__dict__["_master"] = [new]
+        return new
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        for k in ("_engines", "_lock", "_master"):
+            st.pop(k, None)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._engines = {}
+        self._lock = threading.Lock()
+        self._master = [self]
+
+    def maps_from_frame(self, img, preprocess, dest_size, factor):
+        """The device-side body of get_outputs (evaluate/coco_eval.py:80-114) for one raw uint8 BGR frame: the frame
+        goes to the GPU as bytes, crop_with_factor (bilinear resize + zero padding, bit-identical to cv2's) and the
+        `preprocess` normalisation run there, fused into the first convolution's load, and only the two final maps come
+        back.  Returns (paf [1,38,h,w], heat [1,19,h,w]) CUDA tensors and im_scale."""
+        import ctypes
+        import numpy as np
+        master = self._master[0]
+        device = next(master.parameters()).device
+        if device.type != "cuda":
+            raise nat.B200PoseError("the model must be on a CUDA device (model.cuda()): this build has no CPU fallback")
+        if self.precision not in nat.MODES:
+            raise ValueError("precision must be one of %s" % list(nat.MODES))
+        net = self._engine(device)
+        net.set_preprocess(preprocess)
+        img = np.ascontiguousarray(img)
+        sh, sw = img.shape[:2]
+        scale, _, (ph, pw) = nat.crop_geometry(sh, sw, dest_size, factor)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream().cuda_stream
+            frame = torch.empty((1, ph, pw, 3), dtype=torch.uint8, device=device)
+            nat.check(nat.lib().b200pose_net_crop_with_factor(net._h, ctypes.c_void_p(img.ctypes.data), 0, 1, sh, sw,
+                                                              int(dest_size), int(factor), ctypes.c_void_p(frame.data_ptr()),
+                                                              1, ctypes.c_void_p(stream)), "b200pose_net_crop_with_factor")
+            paf = torch.empty((1, 38, ph // 8, pw // 8), dtype=torch.float32, device=device)
+            heat = torch.empty((1, 19, ph // 8, pw // 8), dtype=torch.float32, device=device)
+            net.forward_u8_ptr(frame.data_ptr(), True, 1, ph, pw, nat.MODES[self.precision],
+                               [0] * 10 + [paf.data_ptr(), heat.data_ptr()], True, stream)
+        return paf, heat, scale
 
     def forward(self, x):
         if not x.is_cuda:

@@ -14,9 +14,6 @@ from oracle import glue_port, pafprocess_oracle, synth
 
 pytestmark = pytest.mark.gpu
 
-PENDING = pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: first hardware run of this "
-                           "Python-level test is round 2 (its C entry points passed in profiles/r01_flip_crop_harness.log)")
-
 
 def test_flip_harness_through_the_c_abi(built):
     """tests/cuda/test_flip.cpp: fused b200pose_infer*_flip == forward x2 + host merge + post_run, bit for bit, in all
@@ -28,8 +25,6 @@ def test_flip_harness_through_the_c_abi(built):
     assert r.returncode == 0 and "FLIP TEST OK" in r.stdout, r.stdout[-2000:]
 
 
-@pytest.mark.xfail(strict=False, reason="multi-scale averaging was written after round 1's GPU budget was spent; first "
-                   "hardware run of resize_cubic_accum_kernel is round 2")
 def test_multiscale_harness_through_the_c_abi(built):
     """Same harness including the multi-scale sections: b200pose_infer_raw_u8_multiscale (flip 0 / 1) == per scale host
     crop + validated forward + host merge + host bicubic resize (shared core) + float32 average + validated post_run."""
@@ -92,7 +87,6 @@ def test_fused_flip_inference_matches_reference_shaped_composition(built, he_sd)
     assert nat.launch_count() > 0
 
 
-@PENDING
 def test_pafprocess_kernels_fuzz_against_the_compiled_reference(built):
     """The limbs / assembly kernels (through the legacy lib.pafprocess surface: joint list + x8 maps, exactly what the
     SWIG module gets) on 80 random inputs the fixtures do not reach - duplicated peaks on one pixel, exact score ties,
@@ -124,7 +118,6 @@ def test_pafprocess_kernels_fuzz_against_the_compiled_reference(built):
     assert humans > 80
 
 
-@PENDING
 def test_crop_with_factor_kernel_matches_reference_golden_and_cv2(built, he_sd):
     eng = pkg_module("engine")
     net = eng.NativeNet(0)                      # crop_with_factor needs no weights
@@ -144,7 +137,6 @@ def test_crop_with_factor_kernel_matches_reference_golden_and_cv2(built, he_sd):
             np.testing.assert_array_equal(out[i], want)
 
 
-@PENDING
 def test_raw_frames_of_mixed_sizes_match_reference_shaped_pipeline(built, he_sd):
     """PoseEngine.infer_images (device crop_with_factor + net + post, frames bucketed by shape) == per image: the
     oracle's crop_with_factor (cv2), the native uint8 forward, the oracle's paf_to_pose."""
@@ -171,8 +163,6 @@ def test_raw_frames_of_mixed_sizes_match_reference_shaped_pipeline(built, he_sd)
     assert total > 0
 
 
-@pytest.mark.xfail(strict=False, reason="multi-scale averaging was written after round 1's GPU budget was spent: its cores "
-                   "are verified on the host (tests/test_host.py), the first hardware run of the kernel is round 2")
 def test_multiscale_flip_averaging_matches_composed_oracle(built, he_sd):
     """BASELINE.json configs[4] (multi-scale 0.5/1.0/1.5/2.0 with L/R flip): PoseEngine.infer_images(scales=..., flip=True)
     == per scale the oracle's crop_with_factor of the frame and of the mirrored frame, the native uint8 forward, then the
@@ -209,7 +199,6 @@ def test_multiscale_flip_averaging_matches_composed_oracle(built, he_sd):
     assert total > 0
 
 
-@PENDING
 def test_every_preprocess_mode_fused_into_conv1_1(built, he_sd):
     """b200pose_net_set_preprocess: the uint8 entry point with 'vgg' / 'inception' / 'ssd' / 'rtpose' fused into the first
     convolution gives the very same maps as the numpy function on the host + the fp32-input entry point (bf16 and fp32

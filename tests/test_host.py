@@ -483,3 +483,55 @@ def test_warp_partition_reproduces_std_sort(built):
         for hi in (np.arange(n), np.arange(n)[::-1], np.minimum(np.arange(n), np.arange(n)[::-1]), np.arange(n) % 2,
                    np.arange(n) % 17):
             check(np.ascontiguousarray(hi))
+
+
+def test_data_parallel_replica_finds_the_master_weights(he_sd):
+    """torch.nn.parallel.replicate builds shallow copies whose `_parameters` are EMPTY; rtpose_model must take its
+    weights and its engine cache from the module that owns them (IndexError in _signature on a replica)."""
+    import copy
+    import pickle
+    import lib.network.rtpose_vgg as m
+    model = m.get_model("vgg19")
+    model.load_state_dict(he_sd)
+
+    def replica_of(mod):          # what replicate() leaves behind, minus the device copies
+        rep = mod._replicate_for_data_parallel()
+        for name, child in mod._modules.items():
+            rep._modules[name] = replica_of(child)
+        return rep
+    rep = replica_of(model)
+    assert len(list(rep.parameters())) == 0 and len(rep.state_dict()) == 0
+    assert rep._master[0] is model and rep._engines is model._engines
+    assert len(rep._master[0]._signature()) == 184
+    # the signature covers every tensor: an in-place edit of any of them invalidates the packed device copy
+    before = model._signature()
+    with torch.no_grad():
+        list(model.parameters())[101].mul_(1.0)
+    assert model._signature() != before
+    # copies own their state
+    c = copy.deepcopy(model)
+    assert c._master[0] is c and c._engines is not model._engines and len(c.state_dict()) == 184
+    d = pickle.loads(pickle.dumps(model))
+    assert d._master[0] is d and torch.equal(d.state_dict()["model0.0.weight"], he_sd["model0.0.weight"])
+
+
+def test_engine_remembers_the_shape_of_each_ticket(built):
+    """Two runs in flight with different batch sizes / frame shapes: fetch(ticket=i) must use run i's (n, H, W)
+    (ADVICE r1).  Pure host logic, exercised on an engine object without native handles."""
+    eng = pkg_module("engine")
+    nat = pkg_module("_native")
+    pe = object.__new__(eng.PoseEngine)
+    pe._shapes, pe._last = {}, None
+
+    class FakePost:
+        t = -1
+
+        def last_ticket(self):
+            return self.t
+    pe.post = FakePost()
+    for t, shape in enumerate([(4, 368, 368), (1, 184, 248), (2, 368, 392)]):
+        pe.post.t = t
+        assert pe._remember(*shape) == t
+    assert pe._shape_of(None) == (2, 368, 392) and pe._shape_of(2) == (2, 368, 392) and pe._shape_of(1) == (1, 184, 248)
+    with pytest.raises(nat.B200PoseError):
+        pe._shape_of(0)          # only the last two runs are retained, like the native result slots

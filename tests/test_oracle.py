@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from conftest import POST_CASES, assert_humans_equal, golden, humans_rows_to_dicts
-from oracle import glue_port, net_port, nms_port, pafprocess_oracle, synth
+from oracle import glue_port, net_exact, net_port, nms_port, pafprocess_oracle, synth
 
 
 def _digest(*arrays):
@@ -16,6 +16,31 @@ def _digest(*arrays):
     for a in arrays:
         h.update(np.ascontiguousarray(a).tobytes())
     return h.hexdigest()[:16]
+
+
+@pytest.mark.parametrize("name", ["net_64", "net_368"])
+def test_exact_order_network_is_pinned_to_the_reference(name, he_sd):
+    """oracle/conv_exact.c (fp32 fused multiply-adds in a defined order) vs the output of the unmodified reference
+    module: a different but equally valid fp32 summation order, so the two agree to a few 1e-5 on O(1) maps."""
+    g = golden(name)
+    hw, seed = int(g["hw"]), int(g["seed"])
+    x = torch.rand((1, 3, hw, hw), generator=torch.Generator().manual_seed(seed)) - 0.5
+    (paf, heat), saved = net_exact.forward(he_sd, x.numpy())
+    assert len(saved) == 12 and paf.shape == g["paf"].shape
+    assert np.abs(paf - g["paf"]).max() < 1e-4 and np.abs(heat - g["heat"]).max() < 1e-4
+    np.testing.assert_allclose([float(np.abs(t).max()) for t in saved], g["stage_absmax"], rtol=1e-4)
+
+
+def test_exact_order_network_is_deterministic_and_thread_count_independent(he_sd, monkeypatch):
+    x = (torch.rand((2, 3, 40, 56), generator=torch.Generator().manual_seed(2)) - 0.5).numpy()
+    _, a = net_exact.forward(he_sd, x)
+    monkeypatch.setenv("ORACLE_THREADS", "1")
+    _, b = net_exact.forward(he_sd, x)
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+    # image rows of a batch are independent
+    _, c = net_exact.forward(he_sd, x[1:2])
+    np.testing.assert_array_equal(c[-1][0], a[-1][1])
 
 
 @pytest.mark.parametrize("name", ["net_64", "net_368"])

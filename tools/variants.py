@@ -16,16 +16,11 @@ import __graft_entry__ as g  # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "bstages4": ["-DB2P_CONV_B_STAGES=4"],          # conv: 16 KB less shared memory (co-residency head-room)
-    "bstages3": ["-DB2P_CONV_B_STAGES=3"],
+    "bstages5": ["-DB2P_CONV_B_STAGES=5"],          # conv: the round-1 weight pipeline depth
     "smem2048": ["-DB2P_SMEM_RANGE=2048"],          # limbs: half the shared key range
     "seq8": ["-DB2P_SEQ_RANGE=8"],
     "seq24": ["-DB2P_SEQ_RANGE=24"],
     "threads256": ["-DB2P_LIMB_THREADS=256"],
-    # co-residency study: conv at 186 KB + one limbs block at ~37 KB fit the 228 KB of an SM, and the
-    # persistent limbs grid keeps it at one block per SM; run with B200POSE_POST_OVERLAP=1 B200POSE_LIMBS_PAF_GLOBAL=1
-    "cores": ["-DB2P_CONV_B_STAGES=3", "-DB2P_SMEM_RANGE=1024", "-DB2P_LIMBS_PERSISTENT=1"],
-    "persist": ["-DB2P_LIMBS_PERSISTENT=1"],        # the persistent limbs grid alone (B200POSE_LIMBS_GRID blocks, default 148)
 }
 
 
