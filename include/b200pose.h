@@ -105,6 +105,9 @@ int b200pose_post_sync(b200pose_post* post);
 /* Diagnostics: out[0..2] = max SM cycles of the limbs kernel phases (scoring, exact sort, greedy) over all blocks since
  * the last reset, out[3] = max candidates of a limb, out[4] = total candidates. */
 int b200pose_post_debug(b200pose_post* post, unsigned long long* out, int n, int reset);
+/* Test hook: sorts n 64-bit candidate keys (high word = ~score bits, low word = pair index) on the device with the
+ * product's sorting kernels - libstdc++'s std::sort order (pafprocess.cpp:97), ties included.  Host pointers. */
+int b200pose_post_debug_sort(b200pose_post* post, const unsigned long long* keys, int n, unsigned long long* out);
 /* OR of the status words of every image of every run since the last reset (sticky accumulator kept on the device):
  * with runs in flight a caller reads only some results back; this proves that no run at all overflowed a capacity
  * (the reference's std::vectors grow without bound, pafprocess.cpp:24-44, so an overflow is a divergence).  < 0 on error. */

@@ -150,6 +150,7 @@ struct b200pose_net {
         std::vector<const void*> buffers;
     };
     bool plan_cache_on = true;
+    bool conv_pair = true;            // tcgen05 cta_group::2 CTA pairs for the N >= 64 layers (B200POSE_CONV_PAIR=0: single CTAs)
     int kn = 0, kH = 0, kW = 0, kmode = -1;      // key of the plan currently held in `plan`
     std::vector<PlanEntry> plan_cache;
     DevBuf<__nv_bfloat16> t1, t2, t3, t4, t5a, t5b, t6, t7, t8, t9, cat, bra, brb, br512;
@@ -252,6 +253,7 @@ int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __n
     a.out_f32[0] = f32_0; a.out_f32[1] = f32_1;
     a.f32_ch[0] = f32c0; a.f32_ch[1] = f32c1;
     a.use_base_offset = 0;
+    a.pair = (net->conv_pair && L.n_tile % 32 == 0 && L.n_tile >= 64) ? 1 : 0;    // heads (N = 48) stay single-CTA
     const __nv_bfloat16* in_lo = nullptr;
     if (net->plan_split) {
         a.split = 1;
@@ -484,6 +486,8 @@ int b200pose_net_create(b200pose_net** out, int cuda_device) {
     net->have.assign(B200POSE_NUM_TENSORS, false);
     const char* pc = getenv("B200POSE_PLAN_CACHE");
     net->plan_cache_on = !(pc && pc[0] == '0');
+    const char* cp = getenv("B200POSE_CONV_PAIR");
+    net->conv_pair = !(cp && cp[0] == '0');
     *out = net;
     return 0;
 }
@@ -671,7 +675,9 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
     p->device = cuda_device;
     // candidate-key pool: 6 Mi entries (48 MB) per image of the batch (capped at 2 GiB) - key slots for every (a, b) pair of the limbs that do not
     // fit shared memory plus partition scratch, i.e. ~2 M pairs per image - capped at 1 GiB; exhausting it sets a status bit (loud error in the Python layer)
-    const long pool = (long)batch_cap * (6L << 20) < (1L << 28) ? (long)batch_cap * (6L << 20) : (1L << 28);
+    // two halves (warp slots + partition scratch / contiguous sorted lists), each with one slot per (a, b) PAIR of every
+    // limb: 8 Mi pairs per image of the batch (random-weight 368x368 maps produce ~1 M), capped at 8 GiB in total
+    const long pool = (long)batch_cap * (16L << 20) < (1L << 30) ? (long)batch_cap * (16L << 20) : (1L << 30);
     cudaError_t e = post_alloc(p->pb, batch_cap, peak_cap, human_cap, pool);
     if (e != cudaSuccess) { delete p; return fail("post_alloc failed: %s", cudaGetErrorString(e)); }
     CU(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
@@ -826,6 +832,16 @@ int b200pose_post_status_accum(b200pose_post* p, int reset) {
     int acc = 0;
     for (int v : h) acc |= v;
     return acc;
+}
+
+int b200pose_post_debug_sort(b200pose_post* p, const unsigned long long* keys, int n, unsigned long long* out) {
+    if (!p || !keys || !out) return fail("debug_sort: null pointer");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->s2));
+    cudaError_t e = post_debug_sort(p->pb, keys, n, out, nullptr);
+    if (e != cudaSuccess) return fail("post_debug_sort: %s", cudaGetErrorString(e));
+    g_launches += 2;
+    return 0;
 }
 
 int b200pose_post_debug(b200pose_post* p, unsigned long long* out, int n, int reset) {

@@ -18,6 +18,13 @@
 //   * Four epilogue warps read TMEM (tcgen05.ld 32x32b), add bias, ReLU, optionally 2x2 max-pool through warp
 //     shuffles, convert to bf16 and store NHWC; the stage heads additionally emit the fp32 NCHW outputs.
 //   * Persistent grid (one CTA per SM), static round-robin tile schedule.
+//   * CTA-PAIR mode (a.pair, template kPair): the grid is launched as clusters of two CTAs on the two SMs of a TPC and the
+//     MMAs are tcgen05.mma.cta_group::2 with M = 256: each CTA keeps its OWN 16x16 pixel tile (own halo patch, own TMEM
+//     accumulators, own epilogue) but the two tiles share the weight slice, so each CTA loads and holds only HALF of the
+//     N rows of B.  Per MMA a CTA's shared memory is read for A (4 KB) + B/2 (2 KB) instead of 8 KB, and the per-tap weight
+//     TMA is 8 KB instead of 16 KB: the single-CTA kernel sits at the 128 B/clk shared-memory limit with N = 128
+//     (68 % tensor-pipe activity measured), the pair does not.  Only the leader CTA issues MMAs; TMA loads of both CTAs
+//     credit the leader's "full" barriers, tcgen05.commit multicasts the "empty" / "accumulator full" arrivals to both.
 #include <cstdio>
 
 #include "conv_tc.cuh"
@@ -30,14 +37,26 @@ namespace {
 
 struct TileCoord {
     int n, y0, x0, g, nt;
+    bool valid;      // pair mode: the odd CTA of the last pair may have no pixel tile (it then computes on zeros)
 };
 
-__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int groups, int tiles_x, int tiles_y) {
+// Single-CTA mode: work item t = one (pixel tile, group, n-tile).  Pair mode: work item t = one (pair of consecutive
+// pixel tiles, group, n-tile); the CTA of rank r takes pixel tile 2 * pair + r.  (n-tile, group) vary fastest so that CTAs
+// running at the same time read the same activation patches from L2.
+template <bool kPair>
+__device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int groups, int tiles_x, int tiles_y, int n_img,
+                                                 int rank) {
     TileCoord c;
     c.nt = t % n_tiles;
     t /= n_tiles;
     c.g = t % groups;
     t /= groups;
+    c.valid = true;
+    if (kPair) {
+        const int pix_tiles = n_img * tiles_y * tiles_x;
+        t = 2 * t + rank;
+        if (t >= pix_tiles) { t = pix_tiles; c.valid = false; }     // -> n = n_img: TMA zero-fills, nothing is stored
+    }
     c.x0 = (t % tiles_x) * kTileW;
     t /= tiles_x;
     c.y0 = (t % tiles_y) * kTileH;
@@ -50,8 +69,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+template <bool kPair>
+__device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     extern __shared__ uint8_t smem_raw[];
+    // pair mode: each weight stage holds half of the N rows, so the same bytes give twice the stages
+    constexpr int kBStages = kPair ? 2 * kNumBStages : kNumBStages;
+    constexpr int kBStride = kPair ? kBStageBytes / 2 : kBStageBytes;
     // SWIZZLE_128B operands need 1024 B alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* patch_smem = smem;
@@ -59,9 +82,9 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * kBStageBytes);
     uint64_t* patch_full = bars;                          // [2]
     uint64_t* patch_empty = bars + kNumPatchStages;       // [2]
-    uint64_t* b_full = bars + 2 * kNumPatchStages;        // [5]
-    uint64_t* b_empty = b_full + kNumBStages;             // [5]
-    uint64_t* acc_full = b_empty + kNumBStages;           // [2]
+    uint64_t* b_full = bars + 2 * kNumPatchStages;        // [kBStages]
+    uint64_t* b_empty = b_full + kBStages;                // [kBStages]
+    uint64_t* acc_full = b_empty + kBStages;              // [2]
     uint64_t* acc_empty = acc_full + 2;                   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -70,11 +93,17 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
 
     const int tiles_x = (a.W + kTileW - 1) / kTileW;
     const int tiles_y = (a.H + kTileH - 1) / kTileH;
-    const int total_tiles = a.n_img * tiles_y * tiles_x * a.groups * a.n_tiles;
+    const int rank = kPair ? (int)cluster_ctarank() : 0;
+    // work items of this CTA (pair mode: of this pair): first, stride, total
+    const int pix_items = kPair ? (a.n_img * tiles_y * tiles_x + 1) / 2 : a.n_img * tiles_y * tiles_x;
+    const int total_tiles = pix_items * a.groups * a.n_tiles;
+    const int work0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int wstep = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int taps = a.ksize * a.ksize;
     const int pad = a.ksize >> 1;
     const uint32_t patch_tx = kPatchPitch * (kTileH + a.ksize - 1) * 128;
-    const uint32_t b_tx = a.n_tile * 128;
+    const int b_rows = kPair ? a.n_tile / 2 : a.n_tile;      // weight rows this CTA loads per tap
+    const uint32_t b_tx = b_rows * 128;
     const int nterms = a.split ? 3 : 1;   // split mode: A_hi*W_hi, A_hi*W_lo, A_lo*W_hi per K block
 
     if (warp == 0 && lane == 0) {
@@ -88,21 +117,23 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                 mbar_init(&patch_full[i], 1);
                 mbar_init(&patch_empty[i], 1);
             }
-            for (int i = 0; i < kNumBStages; ++i) {
+            for (int i = 0; i < kBStages; ++i) {
                 mbar_init(&b_full[i], 1);
                 mbar_init(&b_empty[i], 1);
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&acc_full[i], 1);
-                mbar_init(&acc_empty[i], 4);   // one arrive per epilogue warp
+                mbar_init(&acc_empty[i], kPair ? 8 : 4);   // one arrive per epilogue warp (of both CTAs of a pair)
             }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, 512);
+        if (kPair) tmem_alloc_pair(tmem_slot, 512);
+        else tmem_alloc(tmem_slot, 512);
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -110,15 +141,21 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
         // =========================== TMA producer: activation halo patches ===========================
         if (lane == 0) {
             uint32_t pi = 0, pph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
+            for (int t = work0; t < total_tiles; t += wstep) {
+                const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank);
                 const int ch0 = a.in_ch_base + tc.g * a.in_ch_group_stride;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
                     for (int plane = 0; plane <= a.split; ++plane) {     // hi plane, then (split mode) the residual plane
                         mbar_wait(&patch_empty[pi], pph ^ 1, 1);
-                        mbar_expect_tx(&patch_full[pi], patch_tx);
-                        tma_load_4d(patch_smem + pi * kPatchBytes, plane ? &a.tm_in_lo : &a.tm_in, &patch_full[pi],
-                                    ch0 + cb * 64, tc.x0 - pad, tc.y0 - pad, tc.n);
+                        if (kPair) {      // both patches of the pair complete on the leader's barrier
+                            if (rank == 0) mbar_expect_tx(&patch_full[pi], 2 * patch_tx);
+                            tma_load_4d_pair(patch_smem + pi * kPatchBytes, plane ? &a.tm_in_lo : &a.tm_in, &patch_full[pi],
+                                             ch0 + cb * 64, tc.x0 - pad, tc.y0 - pad, tc.n);
+                        } else {
+                            mbar_expect_tx(&patch_full[pi], patch_tx);
+                            tma_load_4d(patch_smem + pi * kPatchBytes, plane ? &a.tm_in_lo : &a.tm_in, &patch_full[pi],
+                                        ch0 + cb * 64, tc.x0 - pad, tc.y0 - pad, tc.n);
+                        }
                         if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; }
                     }
                 }
@@ -128,29 +165,34 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
         // =========================== TMA producer: weight slices ===========================
         if (lane == 0) {
             uint32_t bi = 0, bph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
-                const int wrow = (tc.g * a.n_tiles + tc.nt) * a.n_tile;
+            for (int t = work0; t < total_tiles; t += wstep) {
+                const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank);
+                const int wrow = (tc.g * a.n_tiles + tc.nt) * a.n_tile + rank * b_rows;   // pair: this CTA's half of N
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
                     for (int term = 0; term < nterms; ++term) {          // W_hi, (split) W_lo, W_hi
                         const int wsel = (term == 1) ? taps : 0;
                         for (int tap = 0; tap < taps; ++tap) {
                             mbar_wait(&b_empty[bi], bph ^ 1, 2);
-                            mbar_expect_tx(&b_full[bi], b_tx);
-                            tma_load_3d(b_smem + bi * kBStageBytes, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap);
-                            if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
+                            if (kPair) {
+                                if (rank == 0) mbar_expect_tx(&b_full[bi], 2 * b_tx);
+                                tma_load_3d_pair(b_smem + bi * kBStride, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap);
+                            } else {
+                                mbar_expect_tx(&b_full[bi], b_tx);
+                                tma_load_3d(b_smem + bi * kBStride, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap);
+                            }
+                            if (++bi == kBStages) { bi = 0; bph ^= 1; }
                         }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
+    } else if (warp == 1 && rank == 0) {
+        // =========================== MMA issuer (pair mode: the leader CTA only) ===========================
         // The whole warp walks the loops (warp-uniform control flow, uniform registers for the descriptors); one
         // elected lane issues the tcgen05 instructions.  A divergent `if (lane == 0)` around the loop makes ptxas wrap
         // every UTCHMMA in an ELECT/BRA.U.ANY uniformisation loop (~2x the issue cost).
         {
-            const uint32_t idesc = make_idesc_bf16_m128(a.n_tile);
+            const uint32_t idesc = kPair ? make_idesc_bf16_m256(a.n_tile) : make_idesc_bf16_m128(a.n_tile);
             // Descriptors are built incrementally: the high words are loop invariants, the low word (address >> 4)
             // only receives small adds per tap / sub-tile / K step.
             const uint64_t adesc_hi = make_sdesc_sw128(0, kPatchPitch * 128, 0);
@@ -159,7 +201,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
             const uint32_t b_lo0 = (smem_u32(b_smem) & 0x3FFFFu) >> 4;
             const uint32_t row_wrap = (kPatchPitch - a.ksize) * 8;     // (16-byte units) jump to the next filter row
             uint32_t pi = 0, pph = 0, bi = 0, bph = 0, ai = 0, aph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = work0; t < total_tiles; t += wstep) {
                 mbar_wait(&acc_empty[ai], aph ^ 1, 3);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + ai * 256;
@@ -174,25 +216,37 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                         for (int tap = 0; tap < taps; ++tap) {
                             mbar_wait(&b_full[bi], bph, 5);
                             tc_fence_after();
-                            const uint32_t b_lo = b_lo0 + bi * (kBStageBytes >> 4);
+                            const uint32_t b_lo = b_lo0 + bi * (kBStride >> 4);
                             if (elect_one()) {
 #pragma unroll
                                 for (int sub = 0; sub < 2; ++sub) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k) {
-                                        umma_bf16(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
-                                                  bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
+                                        if (kPair)
+                                            umma_bf16_pair(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
+                                                           bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
+                                        else
+                                            umma_bf16(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
+                                                      bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
                                     }
                                 }
-                                umma_commit(&b_empty[bi]);
-                                if (tap == taps - 1) {
-                                    if (release_patch) umma_commit(&patch_empty[pi]);
-                                    if (cb == a.cin_blocks - 1 && term == nterms - 1) umma_commit(&acc_full[ai]);
+                                if (kPair) {
+                                    umma_commit_pair(&b_empty[bi]);
+                                    if (tap == taps - 1) {
+                                        if (release_patch) umma_commit_pair(&patch_empty[pi]);
+                                        if (cb == a.cin_blocks - 1 && term == nterms - 1) umma_commit_pair(&acc_full[ai]);
+                                    }
+                                } else {
+                                    umma_commit(&b_empty[bi]);
+                                    if (tap == taps - 1) {
+                                        if (release_patch) umma_commit(&patch_empty[pi]);
+                                        if (cb == a.cin_blocks - 1 && term == nterms - 1) umma_commit(&acc_full[ai]);
+                                    }
                                 }
                             }
                             __syncwarp();
                             accumulate = 1;
-                            if (++bi == kNumBStages) { bi = 0; bph ^= 1; }
+                            if (++bi == kBStages) { bi = 0; bph ^= 1; }
                             a_lo += 8;                                            // next tap: one pixel (128 B) to the right
                             if (++dx == a.ksize) { dx = 0; a_lo += row_wrap; }
                         }
@@ -202,7 +256,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
                 if (++ai == 2) { ai = 0; aph ^= 1; }
             }
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         // =========================== epilogue (warps 2..5) ===========================
         // (warp & 3) = 2,3,0,1: each warp may only touch its own quarter of the 128 TMEM lanes.
         const int q = warp & 3;   // TMEM lane quarter this warp may access
@@ -211,8 +265,8 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
         const int Ho = a.pool ? a.H >> 1 : a.H;
         const int Wo = a.pool ? a.W >> 1 : a.W;
         uint32_t ai = 0, aph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const TileCoord tc = decode_tile(t, a.n_tiles, a.groups, tiles_x, tiles_y);
+        for (int t = work0; t < total_tiles; t += wstep) {
+            const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank);
             mbar_wait(&acc_full[ai], aph, 6);
             tc_fence_after();
             const int ch_tile = tc.nt * a.n_tile;                    // first channel of this n-tile within the group
@@ -224,7 +278,7 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
             for (int sub = 0; sub < 2; ++sub) {
                 const int y = tc.y0 + h_in;
                 const int x = tc.x0 + sub * 8 + w_in;
-                const bool valid = (y < a.H) && (x < a.W);
+                const bool valid = tc.valid && (y < a.H) && (x < a.W);
                 // pooled: lanes with even (h, w) own the 2x2 window
                 const bool writer = a.pool ? (valid && !(lane & 1) && !(lane & 8)) : valid;
                 const int yo = a.pool ? y >> 1 : y;
@@ -306,17 +360,31 @@ __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[ai]);
+            if (lane == 0) {
+                if (kPair) mbar_arrive_leader(&acc_empty[ai]);     // the leader's MMA warp waits for both CTAs' epilogues
+                else mbar_arrive(&acc_empty[ai]);
+            }
             if (++ai == 2) { ai = 0; aph ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all();      // both CTAs are done with each other's barriers / the pair's TMEM
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (kPair) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
+}
+
+__global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+    conv_tc_body<false>(a);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvTcThreads, 1)
+    conv_tc_pair_kernel(const __grid_constant__ ConvTcArgs a) {
+    conv_tc_body<true>(a);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -346,6 +414,7 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
     if (a.n_tile % 16 != 0 || a.n_tile < 16 || a.n_tile > 128) return cudaErrorInvalidValue;
     if (a.groups < 1 || a.groups > 2 || in_cstride % 8 != 0) return cudaErrorInvalidValue;
     if (a.split && in_lo == nullptr) return cudaErrorInvalidValue;
+    if (a.pair && (a.n_tile % 32 != 0)) return cudaErrorInvalidValue;     // each CTA of a pair holds n_tile / 2 rows of B
     for (int plane = 0; plane <= (a.split ? 1 : 0); ++plane) {
         cuuint64_t dims[4] = {(cuuint64_t)in_cstride, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n_img};
         cuuint64_t strides[3] = {(cuuint64_t)in_cstride * 2, (cuuint64_t)a.W * in_cstride * 2,
@@ -367,7 +436,7 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
         const int taps = a.ksize * a.ksize;
         cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)rows, (cuuint64_t)(2 * taps)};
         cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)rows * cin_pad * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)a.n_tile, 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)(a.pair ? a.n_tile / 2 : a.n_tile), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&a.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(w), dims, strides,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -381,14 +450,22 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
 }
 
 cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream) {
-    static DynSmemOptIn optin;      // per device: a second net on another GPU of the same process needs its own opt-in
+    static DynSmemOptIn optin, optin_pair;   // per device: a second net on another GPU of the same process needs its own opt-in
+    if (a.pool && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
+    const int tiles_x = (a.W + kTileW - 1) / kTileW;
+    const int tiles_y = (a.H + kTileH - 1) / kTileH;
+    if (a.pair) {
+        cudaError_t e = optin_pair.ensure(conv_tc_pair_kernel, kConvTcSmemBytes);
+        if (e != cudaSuccess) return e;
+        const int pairs = ((a.n_img * tiles_y * tiles_x + 1) / 2) * a.groups * a.n_tiles;
+        const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+        conv_tc_pair_kernel<<<2 * clusters, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);   // __cluster_dims__(2,1,1)
+        return cudaGetLastError();
+    }
     {
         cudaError_t e = optin.ensure(conv_tc_kernel, kConvTcSmemBytes);
         if (e != cudaSuccess) return e;
     }
-    if (a.pool && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
-    const int tiles_x = (a.W + kTileW - 1) / kTileW;
-    const int tiles_y = (a.H + kTileH - 1) / kTileH;
     const int total = a.n_img * tiles_y * tiles_x * a.groups * a.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
     conv_tc_kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);

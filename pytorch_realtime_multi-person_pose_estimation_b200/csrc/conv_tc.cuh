@@ -49,9 +49,12 @@ struct ConvTcArgs {
     // ---- split-precision ("bf16x3") mode: operands are hi + lo bf16 planes, three MMA terms per K block
     int split;                // 0: plain bf16; 1: A_hi*W_hi + A_hi*W_lo + A_lo*W_hi
     __nv_bfloat16* out_lo;    // residual plane of the output (same geometry as `out`), split mode only
+    // ---- CTA-pair mode (tcgen05 cta_group::2): clusters of two CTAs share each weight slice; needs n_tile % 32 == 0
+    int pair;
     // ---- tensor maps
     CUtensorMap tm_in;        // 4D (C, W, H, N) bf16, box (64, 24, 16+ks-1, 1), SWIZZLE_128B
     CUtensorMap tm_w;         // 3D (cin_pad, groups*n_tiles*n_tile, 2*taps) bf16 [hi taps | lo taps], box (64, n_tile, 1)
+                              // (pair mode: box (64, n_tile / 2, 1) - each CTA of a pair loads its half of the N rows)
     CUtensorMap tm_in_lo;     // residual plane of the input (split mode)
 };
 

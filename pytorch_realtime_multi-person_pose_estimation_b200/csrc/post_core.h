@@ -58,17 +58,30 @@ struct PafView {
 B2P_HD int round_half_up(float v) { return v == 0x1.fffffep-2f ? 0 : (int)f_add(v, 0.5f); }
 
 // Scores one (a, b) peak pair of a limb.  Returns true and the candidate score if it passes both criteria.
-B2P_HD bool pair_score(const PafView& paf, int c1, int c2, int ax, int ay, int bx, int by, int h_up, float* score_out) {
+// `Paf` is any accessor with `float at(int c, int y, int x) const` (PafView, or the shared-memory planes of the scoring
+// kernel).  Restated from pafprocess.cpp:57-94 operation for operation, with two EXACT simplifications of its double
+// precision parts (both proven below and pinned by the host tests against the compiled reference):
+//   * `norm < 1e-12` (double):  norm = sqrt(dx^2 + dy^2) of integer dx, dy is 0 or >= 1, so the test is `norm == 0`.
+//   * the length penalty  pen = 0.5*h_up/norm - 1.0 (double), crit2 = (float)((double)(scores/10) + min(pen, 0)):
+//     q = fl(0.5*h_up/norm) < 1  <=>  norm > 0.5*h_up, because 1 - 0.5*h_up/norm is either <= 0 or >= 2^-25 (norm is a
+//     float, 0.5*h_up a multiple of 0.5 below 2^24), far from the 2^-54 rounding boundary below 1; and q - 1.0 is exact
+//     (Sterbenz).  So without penalty crit2 is (float)(double)(scores/10) = scores/10 itself, and the double expression
+//     is evaluated only for pairs longer than half the image height.
+template <class Paf>
+B2P_HD bool pair_score_t(const Paf& paf, int c1, int c2, int ax, int ay, int bx, int by, int h_up, float* score_out) {
     const int dxi = bx - ax, dyi = by - ay;
     float vx = (float)dxi, vy = (float)dyi;
     const float norm = f_sqrt(f_add(f_mul(vx, vx), f_mul(vy, vy)));
-    if ((double)norm < 1e-12) return false;
+    if (!(norm > 0.f)) return false;
     vx = f_div(vx, norm);
     vy = f_div(vy, norm);
     const float step_x = f_div((float)dxi, (float)kStepPaf);
     const float step_y = f_div((float)dyi, (float)kStepPaf);
     float scores = 0.0f;
     int crit1 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int i = 0; i < kStepPaf; ++i) {
         const int lx = round_half_up(f_add((float)ax, f_mul((float)i, step_x)));
         const int ly = round_half_up(f_add((float)ay, f_mul((float)i, step_y)));
@@ -76,13 +89,20 @@ B2P_HD bool pair_score(const PafView& paf, int c1, int c2, int ax, int ay, int b
         scores = f_add(scores, s);
         if (s > 0.05f) crit1 += 1;
     }
-    const double pen = 0.5 * h_up / (double)norm - 1.0;
-    const float crit2 = (float)((double)f_div(scores, (float)kStepPaf) + (pen < 0.0 ? pen : 0.0));
-    if (crit1 > 6 && crit2 > 0.f) {
+    if (crit1 <= 6) return false;
+    float crit2 = f_div(scores, (float)kStepPaf);
+    if (norm > 0.5f * (float)h_up) {
+        const double pen = 0.5 * h_up / (double)norm - 1.0;
+        crit2 = (float)((double)crit2 + pen);
+    }
+    if (crit2 > 0.f) {
         *score_out = crit2;
         return true;
     }
     return false;
+}
+B2P_HD bool pair_score(const PafView& paf, int c1, int c2, int ax, int ay, int bx, int by, int h_up, float* score_out) {
+    return pair_score_t(paf, c1, c2, ax, ay, bx, by, h_up, score_out);
 }
 
 // Candidate key: high 32 bits = ~bits(score) (score > 0, so ascending key == descending score), low 32 bits =

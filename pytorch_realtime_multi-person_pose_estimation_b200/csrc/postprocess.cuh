@@ -1,6 +1,6 @@
 // Fused post-processing kernel family (device-resident replacement of NMS + pafprocess):
 //   peaks_kernel    : find_peaks + NMS refinement      /root/reference/lib/utils/paf_to_pose.py:25-38, 67-145
-//   limbs_kernel    : candidate scoring + greedy match  /root/reference/lib/pafprocess/pafprocess.cpp:47-125
+//   limbs.cu family : candidate scoring + std::sort + greedy match  /root/reference/lib/pafprocess/pafprocess.cpp:47-125
 //   assemble_kernel : person assembly + prune + getters /root/reference/lib/pafprocess/pafprocess.cpp:127-218
 #pragma once
 #include <cstdint>
@@ -9,6 +9,24 @@
 #include "post_core.h"
 
 namespace b2p {
+
+constexpr int kLimbChunkPairs = 2048;    // (a, b) pairs per scoring work item
+constexpr int kLimbSmemRange = 4096;     // candidate keys sorted per shared-memory range
+#ifndef B2P_LANE_SORT_KEYS
+#define B2P_LANE_SORT_KEYS 64            // segments of at most this many keys are finished by one lane each (limbs.cu)
+#endif
+
+struct LimbPlan {         // per (image, limb), written by limb_plan_kernel
+    int na, nb;           // peaks of the two parts (0 / 0: no pairs, or the candidate pool is exhausted)
+    int nchunks;          // scoring work items of this limb
+    int work0;            // index of its first work item
+    int n;                // candidates that passed both criteria (limb_gather_kernel)
+    long long region;     // first slot of the limb's na*nb + 2 slots in pool A (warp slots / partition scratch) and pool B
+};
+struct SortRange {        // one shared-memory sort job: pool[off, off + len), introsort depth budget
+    long long off;
+    int len, depth;
+};
 
 struct PostBuffers {
     // capacities
@@ -32,9 +50,14 @@ struct PostBuffers {
     float* id_score;    // [B][18*peak_cap]   peak score by id
     int* id_xy;         // [B][18*peak_cap][2]
     int row_cap;
-    // candidate pool
+    // candidate keys: pool[0, pool_cap/2) = pool A, pool[pool_cap/2, pool_cap) = pool B (limbs.cu)
     unsigned long long* pool;
-    unsigned long long* pool_cursor;
+    LimbPlan* lplan;    // [B][19]
+    int* sub_cnt;       // [work_cap][8] candidates per warp slot of a scoring work item
+    int* sub_off;       // [work_cap][8] their offsets in the limb's contiguous list
+    int* cursors;       // [4] scoring work cursor, scoring work items, ranges emitted, range cursor
+    SortRange* ranges;  // [range_cap]
+    int work_cap, range_cap;
     // results
     int* n_humans;      // [B]
     float* humans;      // [B][human_cap][1 + 18*4]: score, then per part (x, y, peak score, cid or -1)
@@ -55,6 +78,9 @@ cudaError_t post_peaks(const PostBuffers& pb, int batch, const float* heat, long
 // paf: fp32 view per image: base + img*p_img, strides (p_ch, p_y, p_x), shift (3: low-res, 0: already upsampled).
 cudaError_t post_limbs(const PostBuffers& pb, int batch, const float* paf, long p_img, long p_ch, long p_y,
                                     long p_x, int shift, int h_up, int lw, int lh, cudaStream_t s);
+// Test hook (limbs.cu): exact std::sort of n host keys through the global-memory partition + shared-memory range kernels.
+cudaError_t post_debug_sort(const PostBuffers& pb, const unsigned long long* keys, int n, unsigned long long* out,
+                            cudaStream_t s);
 // Person assembly of the connections post_limbs() left in `pb`.  Small footprint (128 threads, human_cap*4 B smem per
 // image): it can run on a second stream next to the convolutions of the following batch.
 cudaError_t post_assemble(const PostBuffers& pb, int batch, cudaStream_t s);

@@ -81,6 +81,40 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cluster of 2, tcgen05 cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// In the shared::cluster window of a CTA pair bit 24 of an address selects the CTA; clearing it addresses the same
+// offset in the LEADER (rank 0) CTA's shared memory (what CUTLASS calls Sm100MmaPeerBitMask).
+constexpr uint32_t kPairLeaderMask = 0xFEFFFFFFu;
+// TMA tile loads issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's mbarrier.
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPairLeaderMask), "r"(c0),
+        "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPairLeaderMask), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// arrive on the barrier at the same offset in the leader CTA (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairLeaderMask) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -94,6 +128,36 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) 
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// cta_group::2 variants: one warp of EACH CTA of the pair executes alloc / dealloc; both get the same column base.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256: rows 0..127 = the leader's A tile / TMEM, 128..255 = the peer's;
+// the N rows of B are split between the two CTAs' shared memories (leader: first half).  Issued by the leader only.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on the mbarrier at this offset in BOTH CTAs once all MMAs issued so far by this thread have completed.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n"
+        ::"r"(smem_u32(bar))
+        : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; A, B both K-major bf16, fp32 accumulate. One thread issues.
@@ -142,6 +206,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // [10,13) B fmt, [15] A major, [16] B major (0 = K), [17,23) N>>3, [24,29) M>>4.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_m128(uint32_t n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// the same with M = 256 (cta_group::2: 128 rows per CTA of the pair)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_m256(uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
 }
 
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows are 128 B (64 bf16) apart inside an

@@ -190,9 +190,11 @@ def humans_to_dicts(rows, width, height):
 class PoseEngine:
     """Fused batched inference on one GPU: images -> humans, maps never leave the device."""
 
-    def __init__(self, state_arrays, device_index=0, mode="bf16", batch_cap=32, peak_cap=1024, human_cap=1024):
-        self.net = NativeNet(device_index)
-        self.net.load_state_dict_arrays(state_arrays)
+    def __init__(self, state_arrays, device_index=0, mode="bf16", batch_cap=32, peak_cap=1024, human_cap=1024, net=None):
+        if net is None:
+            net = NativeNet(device_index)
+            net.load_state_dict_arrays(state_arrays)
+        self.net = net
         self.post = NativePost(device_index, batch_cap, peak_cap, human_cap)
         self.mode = nat.MODES[mode]
         self.device_index = device_index
@@ -217,6 +219,28 @@ class PoseEngine:
         if ticket not in (self.__dict__.get("_shapes") or {}):
             raise nat.B200PoseError("ticket %r is not one of the last two runs" % (ticket,))
         return self._shapes[ticket]
+
+    @classmethod
+    def from_net(cls, net, mode="bf16", batch_cap=32, peak_cap=1024, human_cap=1024):
+        """An engine around an existing NativeNet (e.g. the one a get_model() module already packed its weights into)."""
+        return cls(None, net.device_index, mode, batch_cap, peak_cap, human_cap, net=net)
+
+    def submit_images(self, images, dest_size=368, factor=8, thresh=0.1, flip=False):
+        """Asynchronous half of infer_images for frames of ONE shape (a video stream): returns a ticket; the frames must
+        stay alive until fetch(ticket=...).  Two submissions may be in flight."""
+        batch = np.ascontiguousarray(np.stack(images))
+        if batch.dtype != np.uint8 or batch.ndim != 4 or batch.shape[3] != 3:
+            raise nat.B200PoseError("submit_images: expected uint8 [h,w,3] frames of one shape")
+        if len(batch) > self.post.batch_cap:
+            raise nat.B200PoseError("submit_images: %d frames exceed batch_cap %d" % (len(batch), self.post.batch_cap))
+        t = self.infer_raw_async_u8(batch.ctypes.data, False, len(batch), batch.shape[1], batch.shape[2], dest_size, factor,
+                                    thresh, flip)
+        if self.__dict__.get("_alive") is None:
+            self._alive = {}
+        self._alive[t] = batch                      # host staging is read asynchronously: keep it until the fetch
+        for old in [k for k in self._alive if k < t - 1]:
+            del self._alive[old]
+        return t
 
     def infer_async(self, in_ptr, in_on_device, n, H, W, thresh=0.1, stream=0):
         nat.check(nat.lib().b200pose_infer(self.net._h, self.post._h, ctypes.c_void_p(in_ptr), int(in_on_device), n, H, W,
@@ -270,7 +294,11 @@ class PoseEngine:
         _, _, (ph, pw) = nat.crop_geometry(src_h, src_w, base_size, factor)
         return self._remember(n, ph, pw)
 
-    def infer_images(self, images, dest_size=368, factor=8, thresh=0.1, flip=False, scales=None):
+    def infer_images_arrays(self, images, dest_size=368, factor=8, thresh=0.1, flip=False, scales=None):
+        """infer_images, but per image the raw person rows (float32 [k, 73], pixel coordinates of the padded frame)."""
+        return self.infer_images(images, dest_size, factor, thresh, flip, scales, _arrays=True)
+
+    def infer_images(self, images, dest_size=368, factor=8, thresh=0.1, flip=False, scales=None, _arrays=False):
         """images: a list of raw uint8 BGR frames of arbitrary (mixed) sizes, as cv2.imread returns them.  Frames are
         bucketed by shape (one launch sequence per bucket, at most batch_cap frames each); returns per-image human lists
         in input order, coordinates normalised to the padded frame like paf_to_pose_cpp's.
@@ -291,8 +319,8 @@ class PoseEngine:
                 else:
                     self.infer_raw_multiscale_async_u8(batch.ctypes.data, False, len(part), sh, sw, scales, dest_size,
                                                        factor, thresh, flip)
-                for i, humans in zip(part, self.fetch()):
-                    out[i] = humans
+                for i, humans in zip(part, self.fetch_arrays() if _arrays else self.fetch()):
+                    out[i] = humans.copy() if _arrays else humans
         return out
 
     def fetch(self, check=True, ticket=None):

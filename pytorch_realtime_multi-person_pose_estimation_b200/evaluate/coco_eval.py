@@ -105,24 +105,56 @@ def eval_coco(outputs, annFile, imgIds):
     return ev.stats[0]
 
 
+EVAL_BATCH = 32      # images per device batch of the batched evaluation loop
+
+
+def _humans_batched(core, images, preprocess):
+    """images (raw BGR frames of mixed sizes) -> per image (humans, heat-map shape): one fused device pass per shape
+    bucket (crop_with_factor, normalisation, network, NMS, PAF matching, assembly - nothing but the person rows comes back)
+    instead of get_outputs + paf_to_pose_cpp per image.  Same kernels, same arithmetic: identical persons."""
+    from .. import _native as nat
+    from ..lib.utils.paf_to_pose import humans_from_rows
+    eng = core.pose_engine(batch_cap=EVAL_BATCH)
+    eng.net.set_preprocess(preprocess)
+    rows = eng.infer_images_arrays(images, cfg.DATASET.IMAGE_SIZE, cfg.MODEL.DOWNSAMPLE,
+                                   float(np.float32(cfg.TEST.THRESH_HEATMAP)))
+    out = []
+    for img, r in zip(images, rows):
+        scale, _, (ph, pw) = nat.crop_geometry(img.shape[0], img.shape[1], cfg.DATASET.IMAGE_SIZE, cfg.MODEL.DOWNSAMPLE)
+        out.append((humans_from_rows(r, pw, ph, cfg.MODEL.NUM_KEYPOINTS), (ph // cfg.MODEL.DOWNSAMPLE, pw // cfg.MODEL.DOWNSAMPLE), scale))
+    return out
+
+
 def run_eval(image_dir, anno_file, vis_dir, model, preprocess):
     """coco_eval.py:245-283: every person image of the annotation file -> get_outputs -> paf_to_pose_cpp ->
-    visualisation written to vis_dir -> COCO records -> mAP."""
+    visualisation written to vis_dir -> COCO records -> mAP.  With a model from this package's get_model() the images
+    are processed EVAL_BATCH at a time by the fused batched engine; any other module takes the
+    reference's image-by-image sequence.  Records, visualisations and printed progress are the same either way."""
     COCO, _ = _pycocotools()
     coco = COCO(anno_file)
     img_ids = coco.getImgIds(catIds=coco.getCatIds(catNms=['person']))
     print("Total number of validation images {}".format(len(img_ids)))
     outputs = []
     print("Processing Images in validation set")
-    for i, img_id in enumerate(img_ids):
-        if i % 10 == 0 and i != 0:
-            print("Processed {} images".format(i))
-        file_name = coco.loadImgs(img_id)[0]['file_name']
-        ori = cv2.imread(os.path.join(image_dir, file_name))
-        paf, heatmap, scale_img = get_outputs(ori, model, preprocess)
-        humans = paf_to_pose_cpp(heatmap, paf, cfg)
-        cv2.imwrite(os.path.join(vis_dir, file_name), draw_humans(ori, humans))
-        upsample_keypoints = (heatmap.shape[0] * cfg.MODEL.DOWNSAMPLE / scale_img,
-                              heatmap.shape[1] * cfg.MODEL.DOWNSAMPLE / scale_img)
-        append_result(img_id, humans, upsample_keypoints, outputs)
+    core = getattr(model, "module", model)
+    batched = hasattr(core, "pose_engine") and preprocess in ('rtpose', 'vgg', 'inception', 'ssd')
+    for c0 in range(0, len(img_ids), EVAL_BATCH):
+        chunk = img_ids[c0:c0 + EVAL_BATCH]
+        names = [coco.loadImgs(img_id)[0]['file_name'] for img_id in chunk]
+        images = [cv2.imread(os.path.join(image_dir, name)) for name in names]
+        if batched:
+            results = _humans_batched(core, images, preprocess)
+        else:
+            results = []
+            for ori in images:
+                paf, heatmap, scale_img = get_outputs(ori, model, preprocess)
+                results.append((paf_to_pose_cpp(heatmap, paf, cfg), heatmap.shape[:2], scale_img))
+        for k, (img_id, name, ori, (humans, hm_shape, scale_img)) in enumerate(zip(chunk, names, images, results)):
+            i = c0 + k
+            if i % 10 == 0 and i != 0:
+                print("Processed {} images".format(i))
+            cv2.imwrite(os.path.join(vis_dir, name), draw_humans(ori, humans))
+            upsample_keypoints = (hm_shape[0] * cfg.MODEL.DOWNSAMPLE / scale_img,
+                                  hm_shape[1] * cfg.MODEL.DOWNSAMPLE / scale_img)
+            append_result(img_id, humans, upsample_keypoints, outputs)
     return eval_coco(outputs=outputs, annFile=anno_file, imgIds=img_ids)

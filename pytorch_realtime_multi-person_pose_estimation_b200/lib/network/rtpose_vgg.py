@@ -98,7 +98,7 @@ class rtpose_model(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engines", "_lock", "_master"):
+            if k in ("_engines", "_lock", "_master", "_pose_engines"):
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         new.__dict__["_engines"] = {}
@@ -108,7 +108,7 @@ class rtpose_model(nn.Module):
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        for k in ("_engines", "_lock", "_master"):
+        for k in ("_engines", "_lock", "_master", "_pose_engines"):
             st.pop(k, None)
         return st
 
@@ -147,6 +147,24 @@ class rtpose_model(nn.Module):
             net.forward_u8_ptr(frame.data_ptr(), True, 1, ph, pw, nat.MODES[self.precision],
                                [0] * 10 + [paf.data_ptr(), heat.data_ptr()], True, stream)
         return paf, heat, scale
+
+    def pose_engine(self, batch_cap=32, peak_cap=2048, human_cap=2048):
+        """The batched fused engine (network + post-processing, maps never leave the device) around this module's native
+        net and weights; cached per (device, precision, capacities).  evaluate.coco_eval.run_eval and the streaming
+        front-ends use it."""
+        from ...engine import PoseEngine
+        master = self._master[0]
+        device = next(master.parameters()).device
+        if device.type != "cuda":
+            raise nat.B200PoseError("the model must be on a CUDA device (model.cuda()): this build has no CPU fallback")
+        net = self._engine(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, self.precision, batch_cap, peak_cap, human_cap)
+        with master._lock:
+            cache = master.__dict__.setdefault("_pose_engines", {})
+            if key not in cache:
+                cache[key] = PoseEngine.from_net(net, self.precision, batch_cap, peak_cap, human_cap)
+            return cache[key]
 
     def forward(self, x):
         if not x.is_cuda:

@@ -47,13 +47,13 @@ def NMS(heatmaps, upsampFactor=1., bool_refine_center=True, bool_gaussian_filt=F
     return [peaks[peaks[:, 4] == j][:, :4].astype(np.float64) for j in range(config.MODEL.NUM_KEYPOINTS)]
 
 
-def paf_to_pose_cpp(heatmaps, pafs, config):
-    post, h, w = _run(heatmaps, pafs, config)
-    W, H = w * config.MODEL.DOWNSAMPLE, h * config.MODEL.DOWNSAMPLE
+def humans_from_rows(rows, W, H, num_keypoints=18):
+    """Person rows of the device ([k, 73]: score, 18 x (x, y, peak score, peak id | -1)) -> the Human / BodyPart objects
+    paf_to_pose_cpp builds (paf_to_pose.py:388-405): coordinates normalised by the network input size."""
     humans = []
-    for human_id, row in enumerate(post.humans(0)):
+    for human_id, row in enumerate(rows):
         human = Human([])
-        for part_idx in range(config.MODEL.NUM_KEYPOINTS):
+        for part_idx in range(num_keypoints):
             x, y, s, cid = row[1 + 4 * part_idx: 5 + 4 * part_idx]
             if cid < 0:
                 continue
@@ -63,3 +63,9 @@ def paf_to_pose_cpp(heatmaps, pafs, config):
             human.score = float(row[0])
             humans.append(human)
     return humans
+
+
+def paf_to_pose_cpp(heatmaps, pafs, config):
+    post, h, w = _run(heatmaps, pafs, config)
+    W, H = w * config.MODEL.DOWNSAMPLE, h * config.MODEL.DOWNSAMPLE
+    return humans_from_rows(post.humans(0), W, H, config.MODEL.NUM_KEYPOINTS)

@@ -127,6 +127,11 @@ extern "C" int core_ties() { return g_ties; }
 extern "C" long core_cand_total() { return g_cand_total; }
 extern "C" long core_cand_needed() { return g_cand_needed; }
 extern "C" int core_sort_mismatch() { return g_sort_mismatch; }
+// libstdc++'s std::sort order of `n` keys (the sequential restatement), for comparisons with the device kernels
+extern "C" void core_seq_sort(const uint64_t* keys, int n, uint64_t* out) {
+    for (int i = 0; i < n; ++i) out[i] = keys[i];
+    seq_std_sort(out, n);
+}
 // direct test hook: sort `n` keys with both formulations, return 0 when identical
 extern "C" int core_sort_check(uint64_t* keys, int n, uint64_t* out) {
     std::vector<uint64_t> seq(keys, keys + n), par(keys, keys + n), blk(keys, keys + n), blk2(keys, keys + n);

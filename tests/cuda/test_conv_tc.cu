@@ -32,7 +32,7 @@ struct Case {
 };
 
 // head: out_ch_off {0,40}, store {40,24}, f32 {38,19}; cout_g is the padded per-group Cout (n_tile).
-static int run_case(const Case& c, int use_bo, int num_sms) {
+static int run_case(const Case& c, int use_bo, int num_sms, int pair) {
     const int taps = c.ks * c.ks, pad = c.ks / 2;
     const int cin_blocks = c.cin_g / 64;
     const int in_c = (c.in_stride_g == 0) ? c.cin_g : c.cin_g * c.groups;
@@ -87,11 +87,12 @@ static int run_case(const Case& c, int use_bo, int num_sms) {
         a.f32_ch[g] = c.head ? valid[g] : 0;
     }
     a.use_base_offset = use_bo;
+    a.pair = pair;
     CK(conv_tc_make_maps(a, d_in, in_c, d_w));
     CK(conv_tc_launch(a, num_sms, 0));
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        printf("case %-28s bo=%d : KERNEL FAILED: %s\n", c.name, use_bo, cudaGetErrorString(e));
+        printf("case %-28s bo=%d pair=%d : KERNEL FAILED: %s\n", c.name, use_bo, pair, cudaGetErrorString(e));
         return 100;
     }
     std::vector<__nv_bfloat16> out_h(out_elems);
@@ -160,14 +161,14 @@ static int run_case(const Case& c, int use_bo, int num_sms) {
                         }
                     }
                 }
-    printf("case %-28s bo=%d : max|err| bf16 %.5f  f32 %.6f  (max|ref| %.3f)  bad=%ld  %s\n", c.name, use_bo, max_err,
-           max_err32, max_ref, bad, bad == 0 ? "OK" : "MISMATCH");
+    printf("case %-28s bo=%d pair=%d : max|err| bf16 %.5f  f32 %.6f  (max|ref| %.3f)  bad=%ld  %s\n", c.name, use_bo, pair,
+           max_err, max_err32, max_ref, bad, bad == 0 ? "OK" : "MISMATCH");
     cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out);
     for (int g = 0; g < 2; ++g) if (d_f32[g]) cudaFree(d_f32[g]);
     return bad == 0 ? 0 : 1;
 }
 
-static void perf(int num_sms, int use_bo) {
+static void perf(int num_sms, int use_bo, int pair) {
     // Mconv{2..5}_stageX_L{1,2}: 7x7 128->128, both branches grouped, batch 32 @46x46.
     struct P { const char* name; int n, H, W, ks, groups, cin_g, stride_g, cout_g, n_tile, pool; };
     const P ps[] = {
@@ -198,6 +199,7 @@ static void perf(int num_sms, int use_bo) {
         a.bias = d_bias; a.relu = 1; a.pool = p.pool; a.out = d_out; a.out_cstride = rows;
         for (int g = 0; g < 2; ++g) { a.out_ch_off[g] = g * p.cout_g; a.store_ch[g] = p.n_tile; }
         a.use_base_offset = use_bo;
+        a.pair = (pair && p.n_tile % 32 == 0) ? 1 : 0;
         CK(conv_tc_make_maps(a, d_in, in_c, d_w));
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -212,7 +214,7 @@ static void perf(int num_sms, int use_bo) {
         cudaEventElapsedTime(&ms, e0, e1);
         ms /= iters;
         double flops = 2.0 * p.n * p.H * p.W * (double)rows * taps * p.cin_g;
-        printf("perf %-30s : %8.3f ms  %8.1f TFLOP/s\n", p.name, ms, flops / ms * 1e-9);
+        printf("perf %-30s pair=%d : %8.3f ms  %8.1f TFLOP/s\n", p.name, a.pair, ms, flops / ms * 1e-9);
         cudaFree(d_in); cudaFree(d_w); cudaFree(d_out); cudaFree(d_bias);
     }
 }
@@ -234,6 +236,8 @@ int main(int argc, char** argv) {
         {"7x7 2grp shared192->128 22x26", 1, 22, 26, 7, 2, 192, 0, 128, 128, 1, 0, 0},
         {"1x1 head 128->38|19 46x46", 2, 46, 46, 1, 2, 128, 128, 48, 48, 0, 0, 1},
         {"1x1 512->512 46x46 4 ntiles", 1, 46, 46, 1, 1, 512, 512, 512, 128, 1, 0, 0},
+        {"3x3 64->128 odd tiles 3x40x16", 3, 40, 16, 3, 1, 64, 64, 128, 128, 1, 0, 0},     // 3 images x 3 x 1 = 9 pixel tiles (odd)
+        {"7x7 2grp 128->128 1x16x16", 1, 16, 16, 7, 2, 128, 128, 128, 128, 1, 0, 0},        // ONE pixel tile: the odd CTA idles
     };
     // use_base_offset=0 is the product setting: the UMMA shared-memory descriptor swizzles on absolute smem address
     // bits, so shifted (non-1024B-aligned) window starts need no phase field.  `probe` also runs the =1 variant
@@ -242,15 +246,17 @@ int main(int argc, char** argv) {
     int fails = 0;
     for (int bo = probe ? 1 : 0; bo >= 0; --bo) {
         for (const Case& c : cases) {
-            int r = run_case(c, bo, sms);
-            if (r >= 100) {   // sticky CUDA error: the context is gone
-                printf("aborting after kernel failure\n");
-                return 3;
+            for (int pair = 0; pair <= ((c.n_tile % 32 == 0) ? 1 : 0); ++pair) {     // CTA-pair mode where it is eligible
+                int r = run_case(c, bo, sms, pair);
+                if (r >= 100) {   // sticky CUDA error: the context is gone
+                    printf("aborting after kernel failure\n");
+                    return 3;
+                }
+                if (bo == 0) fails += r;
             }
-            if (bo == 0) fails += r;
         }
     }
     printf("conv_tc: %s\n", fails == 0 ? "ALL OK" : "FAILURES");
-    if (do_perf) perf(sms, 0);
+    if (do_perf) { perf(sms, 0, 0); perf(sms, 0, 1); }
     return fails == 0 ? 0 : 1;
 }

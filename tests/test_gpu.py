@@ -185,6 +185,40 @@ def test_post_kernels_vs_oracle_and_reference_golden(name, built):
     print(name, "peaks", len(jl), "humans", len(got), "status", post.status(0))
 
 
+def test_device_sort_kernels_reproduce_std_sort(built):
+    """The product's sorting stages (global-memory partitions above 4096 keys, level-synchronous shared-memory introsort
+    below) against the sequential restatement of libstdc++'s std::sort, INCLUDING the order of equal keys, on duplicate-
+    heavy and adversarial inputs (sorted / reversed / organ pipe / few distinct values) of every size class."""
+    import ctypes
+    eng, nat = pkg_module("engine"), pkg_module("_native")
+    host = ctypes.CDLL(os.path.join(ROOT, "build", "libpostcore_host.so"))
+    U = ctypes.POINTER(ctypes.c_uint64)
+    host.core_seq_sort.argtypes = [U, ctypes.c_int, U]
+    post = eng.NativePost(0, batch_cap=1, peak_cap=64, human_cap=16)
+    rs = np.random.RandomState(0)
+    checked = 0
+
+    def check(hi):
+        nonlocal checked
+        n = len(hi)
+        keys = (hi.astype(np.uint64) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+        want, got = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        host.core_seq_sort(keys.ctypes.data_as(U), n, want.ctypes.data_as(U))
+        nat.check(nat.lib().b200pose_post_debug_sort(post._h, keys.ctypes.data, n, got.ctypes.data), "debug_sort")
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, "n=%d: first mismatch at %d of %d (%d wrong)" % (n, bad[0], n, bad.size)
+        checked += 1
+    for n in [1, 2, 3, 15, 16, 17, 18, 31, 32, 33, 64, 65, 100, 257, 1000, 2048, 4095, 4096, 4097, 5000, 9000, 20000,
+              70000, 300000]:
+        for distinct in (1, 2, 7, max(1, n // 3), 1 << 30):
+            check(rs.randint(0, distinct, size=n))
+    for n in (17, 33, 100, 1000, 4096, 5000, 50000):
+        for hi in (np.arange(n), np.arange(n)[::-1], np.minimum(np.arange(n), np.arange(n)[::-1]), np.arange(n) % 2,
+                   np.arange(n) % 17, (np.arange(n) * 7919) % 1013):
+            check(np.ascontiguousarray(hi))
+    print("device std::sort: %d inputs identical to the sequential restatement" % checked)
+
+
 def test_post_batch_and_nchw_layout(built):
     eng = pkg_module("engine")
     maps = [synth.stick_figures(p, s)[:2] for p, s in ((2, 21), (6, 22), (12, 23), (1, 24))]

@@ -535,3 +535,53 @@ def test_engine_remembers_the_shape_of_each_ticket(built):
     assert pe._shape_of(None) == (2, 368, 392) and pe._shape_of(2) == (2, 368, 392) and pe._shape_of(1) == (1, 184, 248)
     with pytest.raises(nat.B200PoseError):
         pe._shape_of(0)          # only the last two runs are retained, like the native result slots
+
+
+def test_pose_stream_pipelines_two_batches(built):
+    """streaming.PoseStream: frames are grouped into batches, batch i+1 is SUBMITTED before batch
+    i is fetched (two runs in flight), results come back in frame order, a trailing partial batch is flushed, frames of
+    different shapes are refused.  Host logic, exercised with a stand-in engine."""
+    streaming = pkg_module("streaming")
+    nat = pkg_module("_native")
+    log = []
+
+    class FakeNet:
+        def set_preprocess(self, name): log.append(("pre", name))
+
+    class FakeEngine:
+        net = FakeNet()
+        t = -1
+
+        def submit_images(self, images, dest, factor, thresh):
+            self.t += 1
+            log.append(("submit", self.t, [int(f[0, 0, 0]) for f in images]))
+            self.last = {self.t: len(images)}
+            FakeEngine.sizes[self.t] = [int(f[0, 0, 0]) for f in images]
+            return self.t
+
+        def fetch_arrays(self, ticket=None):
+            log.append(("fetch", ticket))
+            rows = []
+            for v in FakeEngine.sizes[ticket]:      # one person per frame whose nose x encodes the frame's value
+                r = np.full((1, 73), -1.0, np.float32)
+                r[0, 0] = 1.0
+                r[0, 1:5] = (v, 2 * v, 0.5, 0)
+                rows.append(r)
+            return rows
+    FakeEngine.sizes = {}
+
+    class FakeModel:
+        def pose_engine(self, batch_cap): log.append(("engine", batch_cap)); return FakeEngine()
+    frames = [np.full((48, 64, 3), i, np.uint8) for i in range(7)]
+    got = list(streaming.PoseStream(FakeModel(), frames, batch=3, draw=False))
+    assert [int(f[0, 0, 0]) for f, _, _ in got] == list(range(7))
+    _, _, (ph, pw) = nat.crop_geometry(48, 64, 368, 8)       # coordinates are normalised by the padded network input
+    assert (ph, pw) == (368, 496)
+    assert [h[0].body_parts[0].x for _, h, _ in got] == [float(np.float32(i)) / pw for i in range(7)]
+    ops = [e[:2] for e in log if e[0] in ("submit", "fetch")]
+    assert ops == [("submit", 0), ("submit", 1), ("fetch", 0), ("submit", 2), ("fetch", 1), ("fetch", 2)]
+    assert log[0] == ("engine", 3) and log[1] == ("pre", "rtpose")
+    with pytest.raises(nat.B200PoseError):
+        list(streaming.PoseStream(FakeModel(), [frames[0], np.zeros((50, 64, 3), np.uint8)], batch=2, draw=False))
+    with pytest.raises(nat.B200PoseError):
+        streaming.PoseStream(object(), frames)

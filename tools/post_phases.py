@@ -21,9 +21,6 @@ nat.lib().b200pose_post_debug(eng.post._h, dbg, 16, 1)
 e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 e[0].record(); eng.infer_async(x.data_ptr(), True, B, 368, 368, 0.1, st); e[1].record(); torch.cuda.synchronize()
 nat.lib().b200pose_post_debug(eng.post._h, dbg, 16, 0)
-print("step %.3f ms; limbs phases (max cycles over blocks): scoring %d sort %d greedy %d ; max cands %d total cands %d"
-      % (e[0].elapsed_time(e[1]), dbg[0], dbg[1], dbg[2], dbg[3], dbg[4]))
-print("sort sums over blocks (Mcycles): levelG partitions %.1f (%d ops), levelS block phase %.1f, levelS warp phase %.1f, total sort %.1f over %d blocks" % (dbg[5]/1e6, dbg[8], dbg[6]/1e6, dbg[7]/1e6, dbg[9]/1e6, dbg[10]))
-print("warp phase detail: %d partition ops, %.1f Mcycles inside partitions, %.1f Mcycles inside warp_descend (all warps summed), %d idle polls" % (dbg[13], dbg[11]/1e6, dbg[12]/1e6, dbg[14]))
+print("step %.3f ms; candidates per batch %d, largest limb %d" % (e[0].elapsed_time(e[1]), dbg[4], dbg[3]))
 res = eng.fetch()
 print("humans per image:", [len(r) for r in res][:8], "status", eng.post.status(0))

@@ -13,15 +13,4 @@ for v in $names; do
   B200POSE_LIB=$lib timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline \
       > gpurun_out/variants/$v.json 2>> gpurun_out/variants/$v.log
 done
-# overlap experiments: the same libraries with the post-processing on the second stream
-for v in base persist cores; do
-  lib=$PWD/build/variants/libb200pose_$v.so
-  [ -f "$lib" ] || continue
-  extra=""; [ "$v" = cores ] && extra="B200POSE_LIMBS_PAF_GLOBAL=1"
-  env B200POSE_LIB=$lib B200POSE_POST_OVERLAP=1 $extra timeout 300 python -m pytest tests/test_gpu.py -x -q -m gpu \
-      -k "post_kernels or fused_engine or two_runs" > gpurun_out/variants/${v}_overlap.log 2>&1
-  echo "${v}_overlap parity rc=$? $(tail -1 gpurun_out/variants/${v}_overlap.log)"
-  env B200POSE_LIB=$lib B200POSE_POST_OVERLAP=1 $extra timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline \
-      > gpurun_out/variants/${v}_overlap.json 2>> gpurun_out/variants/${v}_overlap.log
-done
 python tools/variants.py report

@@ -17,10 +17,6 @@ import __graft_entry__ as g  # noqa: E402
 VARIANTS = {
     "base": [],
     "bstages5": ["-DB2P_CONV_B_STAGES=5"],          # conv: the round-1 weight pipeline depth
-    "smem2048": ["-DB2P_SMEM_RANGE=2048"],          # limbs: half the shared key range
-    "seq8": ["-DB2P_SEQ_RANGE=8"],
-    "seq24": ["-DB2P_SEQ_RANGE=24"],
-    "threads256": ["-DB2P_LIMB_THREADS=256"],
 }
 
 
