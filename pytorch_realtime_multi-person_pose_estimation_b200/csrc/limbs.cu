@@ -44,30 +44,26 @@ static_assert(kSubPerChunk * 32 == kScoreThreads, "one warp per sub-chunk");
 constexpr int kGatherThreads = 512, kGatherWarps = kGatherThreads / 32;
 constexpr int kS = kLimbSmemRange;             // keys per shared-memory range
 constexpr int kSortThreads = 512, kSortWarps = kSortThreads / 32;
-constexpr int kRowsMax = kS / 32, kRowsPerWarp = kRowsMax / kSortWarps;
-constexpr int kActMax = kS / 17 + 2;
 constexpr int kGreedyThreads = 512, kGreedySeg = 2048, kGreedyPer = kGreedySeg / kGreedyThreads;
 constexpr int kBigStack = 96;
+constexpr int kBalRows = 4096;                 // ballot cache of the global-memory partitions: up to 131072 keys
 
 __device__ __forceinline__ uint32_t key_hi(const unsigned long long* keys, int i) {
     return reinterpret_cast<const uint32_t*>(keys)[2 * i + 1];
 }
-__device__ __forceinline__ uint32_t bits_le(int lane) { return 0xFFFFFFFFu >> (31 - lane); }          // bits 0..lane
-__device__ __forceinline__ uint32_t bits_range(int lo, int hi) { return (0xFFFFFFFFu >> (31 - hi)) & (0xFFFFFFFFu << lo); }
 
 // Longest-job-first: block `rank` of an image takes the limb with the rank-th largest number of (a, b) pairs.
-__device__ __forceinline__ int limb_of_rank(const PostBuffers& pb, int img, int rank_y) {
-    int pairs[kNumLimb];
-#pragma unroll
-    for (int l = 0; l < kNumLimb; ++l)
-        pairs[l] = pb.counts[img * kNumPart + c_lparts[l][0]] * pb.counts[img * kNumPart + c_lparts[l][1]];
-    int limb = rank_y;
-    for (int l = 0; l < kNumLimb; ++l) {
-        int rank = 0;
-        for (int m = 0; m < kNumLimb; ++m) rank += (pairs[m] > pairs[l]) || (pairs[m] == pairs[l] && m < l);
-        if (rank == rank_y) limb = l;
+// One warp: lane l ranks limb l.
+__device__ __forceinline__ int limb_of_rank_warp(const PostBuffers& pb, int img, int rank_y) {
+    const int lane = threadIdx.x & 31;
+    const int mine = lane < kNumLimb ? pb.counts[img * kNumPart + c_lparts[lane][0]] * pb.counts[img * kNumPart + c_lparts[lane][1]] : -1;
+    int rank = 0;
+    for (int m = 0; m < kNumLimb; ++m) {
+        const int pm = __shfl_sync(0xffffffffu, mine, m);
+        rank += (pm > mine) || (pm == mine && m < lane);
     }
-    return limb;
+    const uint32_t hit = __ballot_sync(0xffffffffu, lane < kNumLimb && rank == rank_y);
+    return hit ? __ffs(hit) - 1 : rank_y;
 }
 
 // ------------------------------------------------------------------ plan
@@ -174,12 +170,19 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(PostBuffers p
     const int hw = lw * lh;
     const uint32_t lt = (1u << lane) - 1u;
     int staged = -1;
-    for (;;) {
-        __syncthreads();                     // the previous item is done with s_item / the staged planes
-        if (tid == 0) s_item = atomicAdd(pb.cursors + 0, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= pb.cursors[1]) return;
+    constexpr int kGroup = 4;      // consecutive work items per grab: they mostly belong to one limb, whose planes stay staged
+    for (int it0 = 0;; ++it0) {
+        const int sub = it0 & (kGroup - 1);
+        if (sub == 0) {
+            __syncthreads();                 // the previous group is done with s_item
+            if (tid == 0) s_item = atomicAdd(pb.cursors + 0, kGroup);
+            __syncthreads();
+        }
+        const int item = s_item + sub;
+        if (item >= pb.cursors[1]) {
+            if (sub == 0) return;
+            continue;                        // tail of the last group (uniform)
+        }
         // the limb of this work item: last plan entry with work0 <= item
         int lo = 0, hi = n_limbs - 1;
         while (lo < hi) {
@@ -195,9 +198,16 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(PostBuffers p
         PafView paf = paf0;
         paf.base += img * p_img;
         if (paf_in_smem && staged != li) {
-            for (int i = tid; i < 2 * hw; i += kScoreThreads) {
-                const int ch = i >= hw, r = i - ch * hw;
-                s_planes[i] = paf.base[(ch ? c2 : c1) * paf.sc + (long)(r / lw) * paf.sy + (long)(r % lw) * paf.sx];
+            __syncthreads();                 // every warp is done with the planes of the previous limb
+            if (paf.sx == 1 && paf.sy == lw) {          // planar maps (the network's NCHW outputs): two contiguous planes
+                const float* p1 = paf.base + c1 * paf.sc;
+                const float* p2 = paf.base + c2 * paf.sc;
+                for (int i = tid; i < hw; i += kScoreThreads) { s_planes[i] = p1[i]; s_planes[hw + i] = p2[i]; }
+            } else {
+                for (int i = tid; i < 2 * hw; i += kScoreThreads) {
+                    const int ch = i >= hw, r = i - ch * hw;
+                    s_planes[i] = paf.base[(ch ? c2 : c1) * paf.sc + (long)(r / lw) * paf.sy + (long)(r % lw) * paf.sx];
+                }
             }
             staged = li;
             __syncthreads();
@@ -242,7 +252,9 @@ struct PartShared {
     unsigned long long scan2[kGatherWarps];
     int ksum;
 };
-__device__ int block_rank_partition(unsigned long long* v, int f, int l, int32_t* tabA, int32_t* tabB, PartShared& sh) {
+template <class PosT>
+__device__ int block_rank_partition(unsigned long long* v, int f, int l, PosT* tabA, PosT* tabB, PartShared& sh,
+                                    uint32_t* bal = nullptr /* optional cache of 2 x rows stop-flag ballots */) {
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u, gt = ~lt & ~(1u << lane);
     if (tid == 0) {       // __move_median_to_first(first, first+1, mid, last-1)
@@ -263,8 +275,11 @@ __device__ int block_rank_partition(unsigned long long* v, int f, int l, int32_t
     for (int r = r0; r < r1; ++r) {
         const int p = base + (r << 5) + lane;
         const uint32_t k = p < l ? (uint32_t)(v[p] >> 32) : 0u;
-        cA += __popc(__ballot_sync(0xffffffffu, p < l && k >= pivot));
-        cB += __popc(__ballot_sync(0xffffffffu, p < l && k <= pivot));
+        const uint32_t mA = __ballot_sync(0xffffffffu, p < l && k >= pivot);
+        const uint32_t mB = __ballot_sync(0xffffffffu, p < l && k <= pivot);
+        if (bal != nullptr && lane == 0) { bal[2 * r] = mA; bal[2 * r + 1] = mB; }
+        cA += __popc(mA);
+        cB += __popc(mB);
     }
     if (lane == 0) sh.scan2[wq] = ((unsigned long long)(unsigned)cB << 32) | (unsigned)cA;
     __syncthreads();
@@ -280,17 +295,17 @@ __device__ int block_rank_partition(unsigned long long* v, int f, int l, int32_t
     int run = offA;
     for (int r = r0; r < r1; ++r) {          // lo-stops ranked from the left
         const int p = base + (r << 5) + lane;
-        const bool st = p < l && (uint32_t)(v[p] >> 32) >= pivot;
-        const uint32_t m = __ballot_sync(0xffffffffu, st);
-        if (st) tabA[run + __popc(m & lt) + 1] = p - f;
+        const uint32_t m = bal != nullptr ? bal[2 * r]
+                                          : __ballot_sync(0xffffffffu, p < l && (uint32_t)(v[p] >> 32) >= pivot);
+        if ((m >> lane) & 1u) tabA[run + __popc(m & lt) + 1] = (PosT)(p - f);
         run += __popc(m);
     }
     run = totB - offB - cB;                  // hi-stops ranked from the right
     for (int r = r1 - 1; r >= r0; --r) {
         const int p = base + (r << 5) + lane;
-        const bool st = p < l && (uint32_t)(v[p] >> 32) <= pivot;
-        const uint32_t m = __ballot_sync(0xffffffffu, st);
-        if (st) tabB[run + __popc(m & gt) + 1] = p - f;
+        const uint32_t m = bal != nullptr ? bal[2 * r + 1]
+                                          : __ballot_sync(0xffffffffu, p < l && (uint32_t)(v[p] >> 32) <= pivot);
+        if ((m >> lane) & 1u) tabB[run + __popc(m & gt) + 1] = (PosT)(p - f);
         run += __popc(m);
     }
     __syncthreads();
@@ -303,11 +318,11 @@ __device__ int block_rank_partition(unsigned long long* v, int f, int l, int32_t
     __syncthreads();
     const int K = sh.ksum;
     for (int k = 1 + tid; k <= K; k += kGatherThreads) {
-        const int ia = f + tabA[k], ib = f + tabB[k];
+        const int ia = f + (int)tabA[k], ib = f + (int)tabB[k];
         const unsigned long long t = v[ia]; v[ia] = v[ib]; v[ib] = t;
     }
-    const int a_next = (K + 1 <= totA) ? f + tabA[K + 1] : l;
-    const int cut = (K > 0 && f + tabB[K] < a_next) ? f + tabB[K] : a_next;
+    const int a_next = (K + 1 <= totA) ? f + (int)tabA[K + 1] : l;
+    const int cut = (K > 0 && f + (int)tabB[K] < a_next) ? f + (int)tabB[K] : a_next;
     __syncthreads();
     return cut;
 }
@@ -353,9 +368,16 @@ __global__ void __launch_bounds__(kGatherThreads) limb_gather_kernel(PostBuffers
     __shared__ PartShared s_part;
     __shared__ int s_carry;
     __shared__ int g_top, g_f[kBigStack], g_l[kBigStack], g_d[kBigStack];
+    __shared__ uint32_t s_bal[2 * kBalRows];        // stop-flag ballots of a partition: passes 2 and 3 do not re-read the keys
+    __shared__ int s_limb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int img = blockIdx.x;
-    const int limb = limb_of_rank(pb, img, blockIdx.y);
+    if (warp == 0) {
+        const int l = limb_of_rank_warp(pb, img, blockIdx.y);
+        if (lane == 0) s_limb = l;
+    }
+    __syncthreads();
+    const int limb = s_limb;
     const int li = img * kNumLimb + limb;
     const LimbPlan pl = pb.lplan[li];
     if (pl.nchunks == 0) return;                                      // no pairs (pl.n stays 0)
@@ -409,7 +431,8 @@ __global__ void __launch_bounds__(kGatherThreads) limb_gather_kernel(PostBuffers
         } else if (d == 0) {
             if (tid == 0) seq_heap_sort(reinterpret_cast<uint64_t*>(keys), f, l);     // depth limit: std::__partial_sort
         } else {
-            const int cut = block_rank_partition(keys, f, l, gA, gB, s_part);
+            const int cut = block_rank_partition<int32_t>(keys, f, l, gA, gB, s_part,
+                                                          (l - f - 1 + 31) / 32 <= kBalRows ? s_bal : nullptr);
             if (tid == 0) {
                 int q = g_top;
                 if (q + 2 <= kBigStack) {
@@ -425,54 +448,47 @@ __global__ void __launch_bounds__(kGatherThreads) limb_gather_kernel(PostBuffers
     }
 }
 
-// ------------------------------------------------------------------ level-synchronous exact introsort in shared memory
+// ------------------------------------------------------------------ exact introsort of one range in shared memory
 // One block sorts one range of n <= kS keys with depth budget d, reproducing __introsort_loop (+ the part of
-// __final_insertion_sort that falls into the range).  Two regimes:
-//
-// (1) LEVEL-SYNCHRONOUS partitions while segments are longer than kLaneT keys.  The keys are walked as ROWS of 32
-//     consecutive positions; warp w owns rows [8w, 8w + 8).  A recursion level partitions ALL such segments at once:
-//       phase A  per row: stop flags (key >= pivot: lo-stop, key <= pivot: hi-stop; pivot = the segment's first key after
-//                the median-of-3 move) as ballots; per warp: the counts needed to chain ranks across warps
-//       phase B  lo-stops ranked from the segment's left, hi-stops from its right (ballot prefix + carries), scattered
-//                into rank -> position tables; the totals land in the tables' slot 0 of the segment
-//       phase C  index k of a segment: swap lo-stop k with hi-stop k while posA[k] < posB[k] (monotone); the last such k
-//                yields the cut = min(posA[K+1], posB[K]) - exactly what the sequential Hoare loop returns
-//       phase D  children: head bits, lengths, depth; median-of-3 (or heap sort when the depth budget is spent)
-//     Rows without a key of an active segment are skipped; rows without a segment boundary take a short path.
-// (2) ONE LANE PER SEGMENT once every segment has <= kLaneT keys: the sequential routine (post_core.h seq_sort_range =
-//     the rest of the introsort recursion + the insertion sort of its leaves) runs on hundreds of segments side by side.
-//     A lane spends ~10 instructions per key and level where the cooperative formulation spends ~150 lane slots, and
-//     below kLaneT keys there are enough segments to keep the lanes busy.
+// __final_insertion_sort that falls into the range).  The recursion is walked LEVEL BY LEVEL (one block barrier per
+// level; the segments of a level are independent), and a segment is partitioned by as many threads as it can feed:
+//   > kWarpSeg keys   the whole block, one segment at a time (block_rank_partition: ranks from ballots + per-warp counts)
+//   > kLaneT keys     ONE WARP per segment, 16 segments side by side: the stop flags of the segment's <= 32 rows are
+//                     ballots held in registers (lane r keeps row r), their prefix sums are two warp scans, the rank ->
+//                     position tables live in the segment's own slice of the table arrays - no block barrier, no queue
+//   <= kLaneT keys    ONE LANE per segment after the last level: the sequential routine (the rest of the recursion + the
+//                     insertion sort of its leaves) on hundreds of segments side by side.  A lane spends ~10 instructions
+//                     per key and level where a cooperative partition spends ~50 lane slots, and below kLaneT keys
+//                     there are enough segments to keep the lanes busy.
+constexpr int kLaneT = B2P_LANE_SORT_KEYS;
+constexpr int kWarpSeg = 1024;                 // <= 32 rows of 32 keys behind the pivot
+constexpr int kSegMax = kS / (kLaneT + 1) + 2;    // segments longer than kLaneT in one level
+constexpr int kSmallMax = kS / 17 + 2;            // segments handed to single lanes: disjoint, more than 16 keys each
+struct Seg { uint16_t f, l; uint8_t d, pad; };
 struct SortSmem {
     unsigned long long keys[kS];
     uint16_t tabA[kS + 32], tabB[kS + 32];
-    uint16_t seg_l[kS];
-    uint8_t seg_d[kS];
-    uint32_t head[kRowsMax], balA[kRowsMax], balB[kRowsMax];
-    uint16_t rowf[kRowsMax];
-    uint32_t rowact[2][kRowsMax / 32];
-    int nact[2];
-    uint16_t cutf[kActMax], cutp[kActMax];
-    int ncut;
-    int w_head[kSortWarps], w_tailA[kSortWarps], w_preB[kSortWarps];
-    int range_idx;
+    Seg segs[2][kSegMax];
+    Seg bigs[2][kS / kWarpSeg + 1];
+    Seg small[kSmallMax];
+    int nseg[2], nbig[2], nsmall;
+    PartShared part;
+    int range_idx, cut;
 };
-constexpr uint8_t kSegDone = 0xFF;      // heap-sorted segment (depth budget spent): finished
-constexpr int kLaneT = B2P_LANE_SORT_KEYS;
 
-// Sequential exact introsort of the small segment v[first, last) with depth budget `depth`: post_core.h's seq_sort_range
-// with 32-bit indices and a stack sized for kLaneT keys (a right part is only stacked when it has more than 16 keys, so a
-// segment of n keys stacks at most n / 17 of them).
+// Sequential exact __introsort_loop of the small segment v[first, last) with depth budget `depth`, by ONE lane: partitions
+// until every part has <= 16 keys (the parts themselves are left to the final insertion pass).  post_core.h's
+// seq_sort_range with 32-bit indices and a stack sized for kLaneT keys (a right part is only stacked when it has more
+// than 16 keys, so a segment of n keys stacks at most n / 17 of them).
 constexpr int kLaneStack = kLaneT / 17 + 2;
-__device__ void lane_sort_segment(unsigned long long* v, int first, int last, int depth) {
+__device__ void lane_partition_segment(unsigned long long* v, int first, int last, int depth) {
     int sf[kLaneStack], sl[kLaneStack], sd[kLaneStack], sp = 1;
     sf[0] = first; sl[0] = last; sd[0] = depth;
     while (sp > 0) {
         --sp;
         int f = sf[sp], l = sl[sp], d = sd[sp];
-        bool heap_sorted = false;
         while (l - f > 16) {
-            if (d == 0) { seq_heap_sort(reinterpret_cast<uint64_t*>(v), f, l); heap_sorted = true; break; }
+            if (d == 0) { seq_heap_sort(reinterpret_cast<uint64_t*>(v), f, l); break; }
             --d;
             const int a = f + 1, b = f + (l - f) / 2, c = l - 1;
             int m;
@@ -490,231 +506,171 @@ __device__ void lane_sort_segment(unsigned long long* v, int first, int last, in
                 ++lo;
             }
             if (l - lo > 16) { sf[sp] = lo; sl[sp] = l; sd[sp] = d; ++sp; }      // sp < kLaneStack: see above
-            else
-                for (int i = lo + 1; i < l; ++i) {                 // leaf: stable insertion sort
-                    const unsigned long long val = v[i];
-                    int j = i;
-                    while (j > lo && B2P_COMP(val, v[j - 1])) { v[j] = v[j - 1]; --j; }
-                    v[j] = val;
-                }
             l = lo;
         }
-        if (!heap_sorted)
-            for (int i = f + 1; i < l; ++i) {
-                const unsigned long long val = v[i];
-                int j = i;
-                while (j > f && B2P_COMP(val, v[j - 1])) { v[j] = v[j - 1]; --j; }
-                v[j] = val;
-            }
     }
 }
 
-// opens segment [f, l) with depth budget d for the level `nx`
-__device__ void seg_open(SortSmem& S, int f, int l, int d, int nx) {
-    if (l - f <= kLaneT) return;                      // finished by one lane in regime (2), with the budget left in seg_d
-    uint64_t* v = reinterpret_cast<uint64_t*>(S.keys);
-    if (d == 0) {
-        seq_heap_sort(v, f, l);
-        S.seg_d[f] = kSegDone;
-        return;
+// files the segment [f, l) with depth budget d (one thread): next level's list, the lanes' list, or - budget spent -
+// heap sort on the spot (std::__partial_sort, rare)
+__device__ void push_segment(SortSmem& S, int f, int l, int d, int nx) {
+    const int m = l - f;
+    if (m <= 16) return;                       // a leaf: the final insertion pass sorts it
+    if (m <= kLaneT) {
+        const int i = atomicAdd(&S.nsmall, 1);
+        S.small[i] = Seg{(uint16_t)f, (uint16_t)l, (uint8_t)d, 0};
+    } else if (d == 0) {
+        seq_heap_sort(reinterpret_cast<uint64_t*>(S.keys), f, l);
+    } else if (m > kWarpSeg) {
+        const int i = atomicAdd(&S.nbig[nx], 1);
+        S.bigs[nx][i] = Seg{(uint16_t)f, (uint16_t)l, (uint8_t)d, 0};
+    } else {
+        const int i = atomicAdd(&S.nseg[nx], 1);
+        S.segs[nx][i] = Seg{(uint16_t)f, (uint16_t)l, (uint8_t)d, 0};
     }
-    const int a = f + 1, b = f + (l - f) / 2, c = l - 1;
-    int m;
-    if (B2P_COMP(v[a], v[b])) m = B2P_COMP(v[b], v[c]) ? b : (B2P_COMP(v[a], v[c]) ? c : a);
-    else m = B2P_COMP(v[a], v[c]) ? a : (B2P_COMP(v[b], v[c]) ? c : b);
-    const uint64_t t = v[f]; v[f] = v[m]; v[m] = t;
-    S.seg_d[f] = (uint8_t)(d - 1);
-    atomicAdd(&S.nact[nx], 1);
-    for (int r = f >> 5; r <= (l - 1) >> 5; ++r) atomicOr(&S.rowact[nx][r >> 5], 1u << (r & 31));
 }
 
-// start of the segment that is open at the beginning of row r0 (= the last head before position 32 r0)
-__device__ __forceinline__ int open_seg_before_row(const SortSmem& S, int r0) {
+// exact partition of keys[f, l), 64 < l - f <= kWarpSeg, by one warp; returns the cut (all lanes)
+__device__ int warp_rank_partition(SortSmem& S, int f, int l) {
     const int lane = threadIdx.x & 31;
-    if (r0 == 0) return 0;
-    for (int base = r0 - 1;; base -= 32) {
-        const int idx = base - lane;
-        const uint32_t w = idx >= 0 ? S.head[idx] : 0u;
-        const uint32_t m = __ballot_sync(0xffffffffu, w != 0u);
-        if (m) {
-            const int src = __ffs(m) - 1;
-            const uint32_t wv = __shfl_sync(0xffffffffu, w, src);
-            return 32 * (base - src) + 31 - __clz(wv);
-        }
-        if (base < 32) return 0;      // position 0 is always a head: not reached
+    unsigned long long* v = S.keys;
+    const uint32_t lt = (1u << lane) - 1u, gt = ~lt & ~(1u << lane);
+    if (lane == 0) {       // __move_median_to_first(first, first+1, mid, last-1)
+        const int a = f + 1, b = f + (l - f) / 2, c = l - 1;
+        int m;
+        if (B2P_COMP(v[a], v[b])) m = B2P_COMP(v[b], v[c]) ? b : (B2P_COMP(v[a], v[c]) ? c : a);
+        else m = B2P_COMP(v[a], v[c]) ? a : (B2P_COMP(v[b], v[c]) ? c : b);
+        const unsigned long long t = v[f]; v[f] = v[m]; v[m] = t;
     }
+    __syncwarp();
+    const uint32_t* kw = reinterpret_cast<const uint32_t*>(v);
+    const uint32_t pivot = kw[2 * f + 1];
+    const int base = f + 1;
+    const int rows = (l - base + 31) >> 5;          // <= 32
+    uint32_t myA = 0u, myB = 0u;                    // stop flags of row `lane`
+    for (int r = 0; r < rows; ++r) {
+        const int p = base + (r << 5) + lane;
+        const uint32_t k = p < l ? kw[2 * p + 1] : 0u;
+        const uint32_t bA = __ballot_sync(0xffffffffu, p < l && k >= pivot);
+        const uint32_t bB = __ballot_sync(0xffffffffu, p < l && k <= pivot);
+        if (lane == r) { myA = bA; myB = bB; }
+    }
+    const int cA = __popc(myA), cB = __popc(myB);
+    int incA = cA, incB = cB;                       // inclusive prefix over rows (A), inclusive suffix (B)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, incA, o);
+        const int tb = __shfl_down_sync(0xffffffffu, incB, o);
+        if (lane >= o) incA += ta;
+        if (lane + o < 32) incB += tb;
+    }
+    const int totA = __shfl_sync(0xffffffffu, incA, 31), totB = __shfl_sync(0xffffffffu, incB, 0);
+    const int preA = incA - cA, sufB = incB - cB;   // lo-stops in earlier rows, hi-stops in later rows
+    uint16_t* tabA = S.tabA + f;
+    uint16_t* tabB = S.tabB + f;
+    for (int r = 0; r < rows; ++r) {
+        const uint32_t bA = __shfl_sync(0xffffffffu, myA, r), bB = __shfl_sync(0xffffffffu, myB, r);
+        const int pa = __shfl_sync(0xffffffffu, preA, r), sb = __shfl_sync(0xffffffffu, sufB, r);
+        const int p = base + (r << 5) + lane;
+        if ((bA >> lane) & 1u) tabA[pa + __popc(bA & lt) + 1] = (uint16_t)p;
+        if ((bB >> lane) & 1u) tabB[sb + __popc(bB & gt) + 1] = (uint16_t)p;
+    }
+    __syncwarp();
+    const int lim = totA < totB ? totA : totB;
+    int c = 0;
+    for (int k = 1 + lane; k <= lim; k += 32) c += (tabA[k] < tabB[k]);       // monotone: the count is K
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    const int K = c;
+    for (int k = 1 + lane; k <= K; k += 32) {
+        const int ia = tabA[k], ib = tabB[k];
+        const unsigned long long t = v[ia]; v[ia] = v[ib]; v[ib] = t;
+    }
+    const int a_next = (K + 1 <= totA) ? (int)tabA[K + 1] : l;
+    const int cut = (K > 0 && (int)tabB[K] < a_next) ? (int)tabB[K] : a_next;
+    __syncwarp();
+    return cut;
 }
 
 __device__ void smem_level_sort(SortSmem& S, int n, int depth) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rows = (n + 31) >> 5;
-    const int r_begin = warp * kRowsPerWarp, r_end = min(rows, r_begin + kRowsPerWarp);
-    for (int i = tid; i < kRowsMax; i += kSortThreads) S.head[i] = 0u;
-    if (tid < 2 * (kRowsMax / 32)) (&S.rowact[0][0])[tid] = 0u;
-    if (tid == 0) { S.nact[0] = 0; S.nact[1] = 0; S.ncut = 0; }
-    __syncthreads();
     if (tid == 0) {
-        S.head[0] = 1u;
-        S.seg_l[0] = (uint16_t)n;
-        S.seg_d[0] = (uint8_t)depth;
-        seg_open(S, 0, n, depth, 0);
+        S.nseg[0] = 0; S.nseg[1] = 0; S.nbig[0] = 0; S.nbig[1] = 0; S.nsmall = 0;
+        push_segment(S, 0, n, depth, 0);
     }
     __syncthreads();
-    const uint32_t* kw = reinterpret_cast<const uint32_t*>(S.keys);
     int level = 0;
     for (int cur = 0;; cur ^= 1) {
-        if (S.nact[cur] == 0) break;
+        const int cnt = S.nseg[cur], nbig = S.nbig[cur];
+        if (cnt == 0 && nbig == 0) break;
         if (++level > 2 * 64 + 8) {      // every level consumes depth budget (<= 2 log2 n <= 64): a bug must trap, not hang the box
-            if (tid == 0) printf("[b200pose] level-synchronous sort did not terminate (n=%d depth=%d)\n", n, depth);
+            if (tid == 0) printf("[b200pose] level-wise sort did not terminate (n=%d depth=%d)\n", n, depth);
             __trap();
         }
         const int nx = cur ^ 1;
-        // ---------------- phase A
-        {
-            int cur_f = open_seg_before_row(S, r_begin);
-            bool seen_head = false;
-            int tailA = 0, preB = 0;
-            for (int r = r_begin; r < r_end; ++r) {
-                const uint32_t hb = S.head[r];
-                if (lane == 0) S.rowf[r] = (uint16_t)cur_f;
-                uint32_t bA = 0u, bB = 0u;
-                if ((S.rowact[cur][r >> 5] >> (r & 31)) & 1u) {
-                    const int p = (r << 5) + lane;
-                    int f = cur_f;
-                    if (hb) {
-                        const uint32_t hle = hb & bits_le(lane);
-                        if (hle) f = (r << 5) + 31 - __clz(hle);
-                    }
-                    const int l = S.seg_l[f];
-                    const bool active = p < n && p > f && l - f > kLaneT && S.seg_d[f] != kSegDone;
-                    const uint32_t pivot = kw[2 * f + 1];
-                    const uint32_t k = kw[2 * min(p, n - 1) + 1];
-                    bA = __ballot_sync(0xffffffffu, active && k >= pivot);
-                    bB = __ballot_sync(0xffffffffu, active && k <= pivot);
-                    if (lane == 0) { S.balA[r] = bA; S.balB[r] = bB; }
-                }
-                if (hb) {
-                    const int first = __ffs(hb) - 1, last = 31 - __clz(hb);
-                    if (!seen_head) { preB += __popc(bB & ((1u << first) - 1u)); seen_head = true; }
-                    tailA = __popc(bA & (0xFFFFFFFFu << last));
-                    cur_f = (r << 5) + last;
-                } else {
-                    if (!seen_head) preB += __popc(bB);
-                    tailA += __popc(bA);
-                }
+        // segments too long for one warp: the whole block, one after the other (only the first levels have any)
+        for (int i = 0; i < nbig; ++i) {
+            const Seg sg = S.bigs[cur][i];
+            const int cut = block_rank_partition<uint16_t>(S.keys, sg.f, sg.l, S.tabA + sg.f, S.tabB + sg.f, S.part);
+            if (tid == 0) {
+                push_segment(S, sg.f, cut, sg.d - 1, nx);
+                push_segment(S, cut, sg.l, sg.d - 1, nx);
             }
-            if (lane == 0) { S.w_head[warp] = seen_head; S.w_tailA[warp] = tailA; S.w_preB[warp] = preB; }
         }
-        __syncthreads();
-        // ---------------- phase B
-        {
-            int carry = 0;
-            for (int v = warp - 1; v >= 0; --v) { carry += S.w_tailA[v]; if (S.w_head[v]) break; }
-            for (int r = r_begin; r < r_end; ++r) {          // lo-stops, ranked from the left
-                if (!((S.rowact[cur][r >> 5] >> (r & 31)) & 1u)) { carry = 0; continue; }
-                const uint32_t hb = S.head[r];
-                const uint32_t bA = S.balA[r];
-                const int p = (r << 5) + lane;
-                int f = S.rowf[r], rank;
-                if (hb == 0u) {
-                    rank = __popc(bA & bits_le(lane)) + carry;
-                    carry += __popc(bA);
-                } else {
-                    const uint32_t hle = hb & bits_le(lane);
-                    const int lo = hle ? 31 - __clz(hle) : 0;
-                    if (hle) f = (r << 5) + lo;
-                    rank = __popc(bA & bits_range(lo, lane)) + (hle ? 0 : carry);
-                    carry = __popc(bA & (0xFFFFFFFFu << (31 - __clz(hb))));
-                }
-                if ((bA >> lane) & 1u) S.tabA[f + rank] = (uint16_t)p;
-                const int l = S.seg_l[f];
-                if (p == l - 1 && l - f > kLaneT && S.seg_d[f] != kSegDone) S.tabA[f] = (uint16_t)rank;     // total
-            }
-            int carryR = 0;
-            for (int v = warp + 1; v < kSortWarps; ++v) { carryR += S.w_preB[v]; if (S.w_head[v]) break; }
-            for (int r = r_end - 1; r >= r_begin; --r) {      // hi-stops, ranked from the right
-                if (!((S.rowact[cur][r >> 5] >> (r & 31)) & 1u)) { carryR = 0; continue; }
-                const uint32_t hb = S.head[r];
-                const uint32_t bB = S.balB[r];
-                const int p = (r << 5) + lane;
-                int f = S.rowf[r], rank;
-                if (hb == 0u) {
-                    rank = __popc(bB & (0xFFFFFFFFu << lane)) + carryR;
-                    carryR += __popc(bB);
-                } else {
-                    const uint32_t hle = hb & bits_le(lane);
-                    if (hle) f = (r << 5) + 31 - __clz(hle);
-                    const uint32_t hgt = lane == 31 ? 0u : (hb & (0xFFFFFFFFu << (lane + 1)));
-                    const int hi = hgt ? __ffs(hgt) - 2 : 31;
-                    rank = __popc(bB & bits_range(lane, hi)) + (hgt ? 0 : carryR);
-                    carryR = __popc(bB & ((1u << (__ffs(hb) - 1)) - 1u));
-                }
-                if ((bB >> lane) & 1u) S.tabB[f + rank] = (uint16_t)p;
-                if (p == f + 1 && (int)S.seg_l[f] - f > kLaneT && S.seg_d[f] != kSegDone) S.tabB[f] = (uint16_t)rank;   // total
+        // the others: one warp each
+        for (int i = warp; i < cnt; i += kSortWarps) {
+            const Seg sg = S.segs[cur][i];
+            const int cut = warp_rank_partition(S, sg.f, sg.l);
+            if (lane == 0) {
+                push_segment(S, sg.f, cut, sg.d - 1, nx);
+                push_segment(S, cut, sg.l, sg.d - 1, nx);
             }
         }
         __syncthreads();
-        // ---------------- phase C
-        for (int r = r_begin; r < r_end; ++r) {
-            if (!((S.rowact[cur][r >> 5] >> (r & 31)) & 1u)) continue;
-            const uint32_t hb = S.head[r];
-            const int p = (r << 5) + lane;
-            int f = S.rowf[r];
-            if (hb) {
-                const uint32_t hle = hb & bits_le(lane);
-                if (hle) f = (r << 5) + 31 - __clz(hle);
-            }
-            const int l = S.seg_l[f];
-            const int k = p - f;
-            if (p < n && k >= 1 && l - f > kLaneT && S.seg_d[f] != kSegDone) {
-                const int totA = S.tabA[f], totB = S.tabB[f];
-                const int lim = totA < totB ? totA : totB;
-                bool ok = false, okn = false;
-                if (k <= lim) {
-                    const int a = S.tabA[p], b = S.tabB[p];
-                    ok = a < b;
-                    if (ok) { const unsigned long long t = S.keys[a]; S.keys[a] = S.keys[b]; S.keys[b] = t; }
-                    if (k + 1 <= lim) okn = S.tabA[p + 1] < S.tabB[p + 1];
-                }
-                if ((ok && !okn) || (k == 1 && !ok)) {
-                    const int K = ok ? k : 0;
-                    const int a_next = (K + 1 <= totA) ? (int)S.tabA[f + K + 1] : l;
-                    const int cut = (K > 0 && (int)S.tabB[f + K] < a_next) ? (int)S.tabB[f + K] : a_next;
-                    const int ci = atomicAdd(&S.ncut, 1);
-                    S.cutf[ci] = (uint16_t)f;
-                    S.cutp[ci] = (uint16_t)cut;
-                }
-            }
-        }
-        __syncthreads();
-        // ---------------- phase D
-        if (tid < S.ncut) {
-            const int f = S.cutf[tid], cut = S.cutp[tid];
-            const int l = S.seg_l[f], d = S.seg_d[f];         // d: already decremented when the segment was opened
-            S.seg_l[f] = (uint16_t)cut;
-            if (cut < l) {
-                atomicOr(&S.head[cut >> 5], 1u << (cut & 31));
-                S.seg_l[cut] = (uint16_t)l;
-                S.seg_d[cut] = (uint8_t)d;
-                seg_open(S, cut, l, d, nx);
-            }
-            seg_open(S, f, cut, d, nx);
-        }
-        __syncthreads();
-        if (tid == 0) { S.ncut = 0; S.nact[cur] = 0; }
-        if (tid < kRowsMax / 32) S.rowact[cur][tid] = 0u;
+        if (tid == 0) { S.nseg[cur] = 0; S.nbig[cur] = 0; }
         __syncthreads();
     }
-    // ---------------- regime (2): every remaining segment (<= kLaneT keys, depth budget seg_d) by one lane
-    for (int p = tid; p < n; p += kSortThreads) {
-        if (!((S.head[p >> 5] >> (p & 31)) & 1u)) continue;
-        const int l = S.seg_l[p], d = S.seg_d[p];
-        if (l - p > 1 && d != kSegDone) lane_sort_segment(S.keys, p, l, d);
+    // one lane per remaining segment of 17..kLaneT keys; lanes of different warps first (lanes of one warp that run
+    // different data-dependent loops serialise each other)
+    for (int i0 = 0; i0 < S.nsmall; i0 += kSortThreads) {
+        const int i = i0 + lane * kSortWarps + warp;
+        if (i < S.nsmall) {
+            const Seg sg = S.small[i];
+            lane_partition_segment(S.keys, sg.f, sg.l, sg.d);
+        }
     }
     __syncthreads();
+    // __final_insertion_sort: every part now has <= 16 keys (or is sorted), parts are ordered among each other, and an
+    // insertion sort is stable - so a key's final position is its rank in the window of +-15 positions around it
+    {
+        const uint32_t* kw = reinterpret_cast<const uint32_t*>(S.keys);
+        constexpr int kPer = kS / kSortThreads;
+        unsigned long long val[kPer];
+        int dst[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int p = j * kSortThreads + tid;
+            dst[j] = -1;
+            val[j] = 0ull;
+            if (p < n) {
+                val[j] = S.keys[p];
+                const uint32_t kp = (uint32_t)(val[j] >> 32);
+                const int lo = p - 15 > 0 ? p - 15 : 0, hi = p + 15 < n - 1 ? p + 15 : n - 1;
+                int c = lo;
+                for (int q = lo; q < p; ++q) c += kw[2 * q + 1] <= kp;
+                for (int q = p + 1; q <= hi; ++q) c += kw[2 * q + 1] < kp;
+                dst[j] = c;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+            if (dst[j] >= 0) S.keys[dst[j]] = val[j];
+        __syncthreads();
+    }
 }
 
-__global__ void __launch_bounds__(kSortThreads) range_sort_kernel(PostBuffers pb) {
+__global__ void __launch_bounds__(kSortThreads, 3) range_sort_kernel(PostBuffers pb) {
     extern __shared__ __align__(16) unsigned char sort_smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(sort_smem_raw);
     const int tid = threadIdx.x;
@@ -779,9 +735,15 @@ __global__ void __launch_bounds__(kGreedyThreads) limb_greedy_kernel(PostBuffers
     __shared__ uint32_t used_a[64], used_b[64];          // peak_cap <= 2048
     __shared__ int scan_scratch[kGreedyThreads / 32 + 1];
     __shared__ int s_nc;
+    __shared__ int s_limb;
     const int tid = threadIdx.x;
     const int img = blockIdx.x;
-    const int limb = limb_of_rank(pb, img, blockIdx.y);
+    if (tid < 32) {
+        const int l = limb_of_rank_warp(pb, img, blockIdx.y);
+        if (tid == 0) s_limb = l;
+    }
+    __syncthreads();
+    const int limb = s_limb;
     const LimbPlan pl = pb.lplan[img * kNumLimb + limb];
     int* out_cnt = pb.conn_cnt + img * kNumLimb + limb;
     const int n = pl.n, nb = pl.nb;

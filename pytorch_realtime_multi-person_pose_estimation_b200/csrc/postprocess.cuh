@@ -11,7 +11,10 @@
 namespace b2p {
 
 constexpr int kLimbChunkPairs = 2048;    // (a, b) pairs per scoring work item
-constexpr int kLimbSmemRange = 4096;     // candidate keys sorted per shared-memory range
+#ifndef B2P_LIMB_SMEM_RANGE
+#define B2P_LIMB_SMEM_RANGE 4096
+#endif
+constexpr int kLimbSmemRange = B2P_LIMB_SMEM_RANGE;     // candidate keys sorted per shared-memory range
 #ifndef B2P_LANE_SORT_KEYS
 #define B2P_LANE_SORT_KEYS 64            // segments of at most this many keys are finished by one lane each (limbs.cu)
 #endif

@@ -17,6 +17,9 @@ import __graft_entry__ as g  # noqa: E402
 VARIANTS = {
     "base": [],
     "bstages5": ["-DB2P_CONV_B_STAGES=5"],          # conv: the round-1 weight pipeline depth
+    "range2048": ["-DB2P_LIMB_SMEM_RANGE=2048"],    # sort ranges of 2048 keys: 26 KB of shared memory, fits next to a conv CTA
+    "lane32": ["-DB2P_LANE_SORT_KEYS=32"],          # one-lane partitions only below 33 keys
+    "lane128": ["-DB2P_LANE_SORT_KEYS=128"],
 }
 
 
