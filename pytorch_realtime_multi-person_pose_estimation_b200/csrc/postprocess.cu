@@ -23,6 +23,13 @@ __constant__ float c_cubic[8][4] = {
     {-0x1.518p-5f, 0x1.fba8p-1f, 0x1.ad8p-5f, -0x1.68p-9f},   {-0x1.7c4p-4f, 0x1.dbb8p-1f, 0x1.7b2p-3f, -0x1.5fp-6f},
     {-0x1.c5cp-4f, 0x1.a308p-1f, 0x1.5efp-2f, -0x1.9c8p-5f},  {-0x1.a94p-4f, 0x1.5918p-1f, 0x1.0568p-1f, -0x1.4acp-4f}};
 
+// the same table as compile-time constants (immediates of the unrolled vertical pass of the interior fast path)
+__device__ constexpr float k_cubic[8][4] = {
+    {-0x1.4acp-4f, 0x1.0568p-1f, 0x1.5918p-1f, -0x1.a94p-4f}, {-0x1.9c8p-5f, 0x1.5efp-2f, 0x1.a308p-1f, -0x1.c5cp-4f},
+    {-0x1.5fp-6f, 0x1.7b2p-3f, 0x1.dbb8p-1f, -0x1.7c4p-4f},   {-0x1.68p-9f, 0x1.ad8p-5f, 0x1.fba8p-1f, -0x1.518p-5f},
+    {-0x1.518p-5f, 0x1.fba8p-1f, 0x1.ad8p-5f, -0x1.68p-9f},   {-0x1.7c4p-4f, 0x1.dbb8p-1f, 0x1.7b2p-3f, -0x1.5fp-6f},
+    {-0x1.c5cp-4f, 0x1.a308p-1f, 0x1.5efp-2f, -0x1.9c8p-5f},  {-0x1.a94p-4f, 0x1.5918p-1f, 0x1.0568p-1f, -0x1.4acp-4f}};
+
 constexpr int kPeakThreads = 256;
 constexpr int kAsmThreads = 128;
 constexpr int kHorStride = 40;   // (2*2+1) * 8
@@ -31,13 +38,72 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ------------------------------------------------------------------ peaks
-__global__ void __launch_bounds__(kPeakThreads) peaks_kernel(PostBuffers pb, const float* __restrict__ heat, long h_img,
+// Interior fast path of the refinement: slots J0 .. J0+NS-1 of this lane (slot j = up-sampled column (lane + 32 j) % 40 of
+// peak (lane + 32 j) / 40 of the group of four).  Horizontal pass into registers, vertical pass fully unrolled, per slot the
+// maximum and the smallest row-major index attaining it.  Arithmetic and operation order: OpenCV's separable INTER_CUBIC.
+template <int J0, int NS>
+__device__ __forceinline__ void refine_interior_slots(const float* plane, int w, const int* px, const int* py,
+                                                      const uint16_t* list, int ni, int grp, int lane, float* best,
+                                                      int* bidx) {
+    float hv[NS][5];
+    int Xs[NS];
+#pragma unroll
+    for (int jj = 0; jj < NS; ++jj) {
+        const int c = lane + 32 * (J0 + jj);               // 0..159: column X of peak g
+        const int g = c >= 120 ? 3 : (c >= 80 ? 2 : (c >= 40 ? 1 : 0));
+        const int X = c - 40 * g;
+        const int gi = grp * 4 + g;
+        Xs[jj] = X;
+        best[J0 + jj] = -INFINITY;
+        bidx[J0 + jj] = 0x7fffffff;
+        if (gi < ni) {
+            const int pk = list[gi];
+            const int x = px[pk], y = py[pk];
+            const int phase = X & 7;
+            const int sx = (X >> 3) + (phase < 4 ? -2 : -1);
+            const int t0 = clampi(sx, 0, 4), t1 = clampi(sx + 1, 0, 4), t2 = clampi(sx + 2, 0, 4), t3 = clampi(sx + 3, 0, 4);
+            const float a0 = c_cubic[phase][0], a1 = c_cubic[phase][1], a2 = c_cubic[phase][2], a3 = c_cubic[phase][3];
+            const float* p0 = plane + (y - 2) * w + (x - 2);
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                const float* prow = p0 + r * w;
+                float v = __fmul_rn(prow[t0], a0);
+                v = __fadd_rn(v, __fmul_rn(prow[t1], a1));
+                v = __fadd_rn(v, __fmul_rn(prow[t2], a2));
+                v = __fadd_rn(v, __fmul_rn(prow[t3], a3));
+                hv[jj][r] = v;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 5; ++r) hv[jj][r] = -INFINITY;     // never wins
+        }
+    }
+#pragma unroll
+    for (int Y = 0; Y < 40; ++Y) {
+        const int phase = Y & 7;
+        const int sy = (Y >> 3) + (phase < 4 ? -2 : -1);
+        const int r0 = sy < 0 ? 0 : (sy > 4 ? 4 : sy), r1 = sy + 1 < 0 ? 0 : (sy + 1 > 4 ? 4 : sy + 1);
+        const int r2 = sy + 2 < 0 ? 0 : (sy + 2 > 4 ? 4 : sy + 2), r3 = sy + 3 < 0 ? 0 : (sy + 3 > 4 ? 4 : sy + 3);
+        const float b0 = k_cubic[phase][0], b1 = k_cubic[phase][1], b2 = k_cubic[phase][2], b3 = k_cubic[phase][3];
+#pragma unroll
+        for (int jj = 0; jj < NS; ++jj) {
+            float v = __fmul_rn(hv[jj][r3], b3);
+            v = __fadd_rn(__fmul_rn(hv[jj][r2], b2), v);
+            v = __fadd_rn(__fmul_rn(hv[jj][r1], b1), v);
+            v = __fadd_rn(__fmul_rn(hv[jj][r0], b0), v);
+            if (v > best[J0 + jj]) { best[J0 + jj] = v; bidx[J0 + jj] = Y * 40 + Xs[jj]; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPeakThreads, 2) peaks_kernel(PostBuffers pb, const float* __restrict__ heat, long h_img,
                                                              long h_ch, long h_y, long h_x, int h, int w, float thresh) {
     extern __shared__ float sm_f[];
     float* plane = sm_f;                       // [h*w]
     float* hor_all = sm_f + h * w;             // [8 warps][5][40]
     __shared__ int warp_cnt[kPeakThreads / 32];
-    __shared__ int s_base;
+    __shared__ int s_base, s_ni, s_nb;
+    __shared__ uint16_t s_list[2048];          // peak indices: interior ones from the front, border ones from the back
     const int part = blockIdx.x, img = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = h * w;
@@ -87,9 +153,58 @@ __global__ void __launch_bounds__(kPeakThreads) peaks_kernel(PostBuffers pb, con
     }
     if (tid == 0) pb.counts[img * kNumPart + part] = n;
 
-    // refinement: 5x5 window (clipped) -> x8 bicubic -> first arg-max        (one warp per peak)
+    // refinement: 5x5 window (clipped) -> x8 bicubic (separable, OpenCV's operation order) -> first arg-max.
+    // Peaks whose window is not clipped (all but the two outermost rows / columns of the map) take the fast path: FOUR
+    // peaks per warp - their 4 x 40 up-sampled columns fill the 32 lanes exactly five times - with the horizontal results in
+    // registers and the vertical pass fully unrolled (tap rows and coefficients are compile-time constants).
+    if (tid == 0) { s_ni = 0; s_nb = 0; }
+    __syncthreads();
+    for (int pk = tid; pk < n; pk += kPeakThreads) {
+        const int x = px[pk], y = py[pk];
+        const bool interior = x >= 2 && x + 2 <= w - 1 && y >= 2 && y + 2 <= h - 1;
+        if (interior) s_list[atomicAdd(&s_ni, 1)] = (uint16_t)pk;
+        else s_list[2047 - atomicAdd(&s_nb, 1)] = (uint16_t)pk;
+    }
+    __syncthreads();
+    const int ni = s_ni, nbd = s_nb;
+    for (int grp = warp; grp * 4 < ni; grp += kPeakThreads / 32) {
+        float best[5];
+        int bidx[5];
+        refine_interior_slots<0, 3>(plane, w, px, py, s_list, ni, grp, lane, best, bidx);
+        refine_interior_slots<3, 2>(plane, w, px, py, s_list, ni, grp, lane, best, bidx);
+        // per peak: maximum value, smallest row-major index among equals (= first arg-max)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float bv = -INFINITY;
+            int bi = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int c = lane + 32 * j;
+                const int gj = c >= 120 ? 3 : (c >= 80 ? 2 : (c >= 40 ? 1 : 0));
+                if (gj == g && (best[j] > bv || (best[j] == bv && bidx[j] < bi))) { bv = best[j]; bi = bidx[j]; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            const int gi = grp * 4 + g;
+            if (lane == 0 && gi < ni) {
+                const int pk = s_list[gi];
+                const int x = px[pk], y = py[pk];
+                const int ay = bi / 40, ax = bi - ay * 40;
+                px[pk] = 8 * (x - 2) + ax;     // == (x+0.5)*8-0.5 + (ax - ((x-x_min+0.5)*8-0.5)), paf_to_pose.py:126-139
+                py[pk] = 8 * (y - 2) + ay;
+                ps[pk] = bv;
+            }
+        }
+        __syncwarp();
+    }
+    // border peaks (clipped window): one warp per peak, rows walked
     float* hor = hor_all + warp * 5 * kHorStride;
-    for (int pk = warp; pk < n; pk += kPeakThreads / 32) {
+    for (int bi_ = warp; bi_ < nbd; bi_ += kPeakThreads / 32) {
+        const int pk = s_list[2047 - bi_];
         const int x = px[pk], y = py[pk];
         const int x_min = max(0, x - 2), x_max = min(w - 1, x + 2);
         const int y_min = max(0, y - 2), y_max = min(h - 1, y + 2);
