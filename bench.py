@@ -117,7 +117,7 @@ def run_ours(args):
     # into the first convolution.  10 rotating device batches (10 x 13 MB > 126 MB L2) + 2 pinned host batches.
     g = torch.Generator().manual_seed(1234 + rank)
     # --raw N: the frames are N x N "camera" frames and crop_with_factor (resize to 368 x 368) runs on the device too
-    SH = SW = args.raw if args.raw else H
+    SH = SW = args.raw if args.raw else H          # (multi-scale: the raw frames are 368 x 368 unless --raw says otherwise)
     host = [torch.randint(0, 256, (BATCH, SH, SW, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
     # enough rotating device batches that one full rotation exceeds the 126 MB L2 (10 at batch 32)
     n_rot = max(10, -(-130_000_000 // (BATCH * SH * SW * 3)))
@@ -130,7 +130,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.raw:
+    scales = [float(v) for v in args.scales.split(",")] if args.scales else None
+    if scales:
+        def infer_u8(ptr, on_device, n, h_, w_, thresh, stream):
+            return eng.infer_raw_multiscale_async_u8(ptr, on_device, n, SH, SW, scales, H, 8, thresh, args.flip, stream)
+    elif args.raw:
         def infer_u8(ptr, on_device, n, h_, w_, thresh, stream):
             return eng.infer_raw_async_u8(ptr, on_device, n, SH, SW, H, 8, thresh, args.flip, stream)
     else:
@@ -203,7 +207,7 @@ def run_ours(args):
     # (resident on the device) instead of the noise a random-weight network emits.  A trained model's maps look like
     # these; the number shows what the step costs when the post-processing is not the pathological case.
     alt = None
-    if rank == 0 and not args.flip and not args.raw and not args.no_alt:
+    if rank == 0 and not args.flip and not args.raw and not args.no_alt and not scales:
         import ctypes
         syn = importlib.import_module(_b200_alias.PKG + ".synthetic")
         heat, paf = syn.person_maps(BATCH, 8, seed=7)
@@ -234,7 +238,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (conv_tc_kernel), measured live: per-launch CUDA events
     roof = None
-    if rank == 0:
+    if rank == 0 and not scales:      # (multi-scale: the plan held at the end is the last scale's, not a 368x368 forward)
         import ctypes
         step_device(0)
         torch.cuda.synchronize()
@@ -283,8 +287,12 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (hi+lo bf16 planes, fp32 accumulate)", "fp32": "f32"}[args.mode],
         "data": "synthetic",
         "config": {"workload": "batch=%d per GPU, 368x368, rtpose VGG19 %s + fused NMS/PAF-match/assembly%s"
-                               % (BATCH, {"bf16": "bf16 (tcgen05)", "bf16x3": "bf16x3 (tcgen05, split precision)", "fp32": "fp32 (CUDA cores, parity mode)"}[args.mode], " (BASELINE.json configs[2]; configs[3] when n_gpus=8)" if BATCH == 32 and not args.flip
-                                  else (", left/right flip test-time averaging on the device (2 forwards per frame)" if args.flip else "")),
+                               % (BATCH, {"bf16": "bf16 (tcgen05)", "bf16x3": "bf16x3 (tcgen05, split precision)", "fp32": "fp32 (CUDA cores, parity mode)"}[args.mode],
+                                  (", multi-scale test-time averaging at scales %s%s (BASELINE.json configs[4]; %d forwards per frame; the "
+                                   "composition has no reference counterpart: parity unpinned, DESIGN.md 2.7)"
+                                   % (args.scales, " x left/right flip" if args.flip else "", len(scales) * (2 if args.flip else 1))) if scales else
+                                  (" (BASELINE.json configs[2]; configs[3] when n_gpus=8)" if BATCH == 32 and not args.flip
+                                   else (", left/right flip test-time averaging on the device (2 forwards per frame)" if args.flip else ""))),
                    "global_batch": BATCH * world, "weights": "He-normal seed 1234 (random init)",
                    "input": ("uint8 HWC BGR %dx%d frames, crop_with_factor (bilinear resize to 368x368) and rtpose_preprocess on "
                              "the device" % (SH, SW)) if args.raw else "uint8 HWC BGR frames, rtpose_preprocess fused on the device",
@@ -298,7 +306,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": (int(np.mean(d2h_bytes)) if d2h_bytes else 0) * world,   # rank 0's count x ranks
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
         "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-        "net_tflops_device": round(FLOPS_PER_FRAME * (2 if args.flip else 1) * frames / (ms_dev * 1e-3) / 1e12 / world, 1),
+        "net_tflops_device": None if scales else round(FLOPS_PER_FRAME * (2 if args.flip else 1) * frames / (ms_dev * 1e-3) / 1e12 / world, 1),
     }
     print(json.dumps(line))
     if world > 1:
@@ -393,6 +401,8 @@ def main():
     ap.add_argument("--no-alt", action="store_true", help="skip the person-like-maps alternative workload")
     ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step (the headline config is 32)")
     ap.add_argument("--flip", action="store_true", help="left/right flip test-time averaging (2 forwards per frame)")
+    ap.add_argument("--scales", default="", metavar="S1,S2,...",
+                    help="multi-scale test-time averaging around 368 (BASELINE.json configs[4]: 0.5,1.0,1.5,2.0 with --flip --batch 8)")
     ap.add_argument("--raw", type=int, default=0, metavar="N",
                     help="feed N x N raw frames and run crop_with_factor (resize to 368 x 368) on the device as well")
     args = ap.parse_args()

@@ -123,7 +123,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&acc_full[i], 1);
-                mbar_init(&acc_empty[i], kPair ? 8 : 4);   // one arrive per epilogue warp (of both CTAs of a pair)
+                mbar_init(&acc_empty[i], kPair ? 16 : 8);   // one arrive per epilogue warp (of both CTAs of a pair)
             }
             fence_mbar_init();
         }
@@ -256,10 +256,14 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 if (++ai == 2) { ai = 0; aph ^= 1; }
             }
         }
-    } else if (warp >= 2 && warp <= 5) {
-        // =========================== epilogue (warps 2..5) ===========================
-        // (warp & 3) = 2,3,0,1: each warp may only touch its own quarter of the 128 TMEM lanes.
+    } else if (warp >= 2 && warp != 6) {
+        // =========================== epilogue (warps 2..5 and 7..10) ===========================
+        // A warp may only touch its own quarter (warp & 3) of the 128 TMEM lanes: warps 2..5 cover quarters 2,3,0,1 and
+        // warps 7..10 cover 3,0,1,2 - two warps per quarter, which split the accumulator columns in 32-column chunks
+        // (even chunks / odd chunks).  With one warp per quarter the layers with little MMA work per tile (Cin = 64, the
+        // 1x1 layers, the pooled layers with their shuffles) were bound by this epilogue.
         const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int half = warp >= 7 ? 1 : 0;
         const int h_in = q * 4 + (lane >> 3);
         const int w_in = lane & 7;
         const int Ho = a.pool ? a.H >> 1 : a.H;
@@ -286,7 +290,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ai * 256 + sub * 128;
                 // 32 accumulator columns per TMEM load (n_tile is a multiple of 16: a 16-column tail handles 48)
 #pragma unroll 1
-                for (int c0 = 0; c0 < a.n_tile; c0 += 32) {
+                for (int c0 = half * 32; c0 < a.n_tile; c0 += 64) {
                     const bool full = (c0 + 32 <= a.n_tile);
                     uint32_t r[32];
                     if (full) tmem_ld32(taddr + c0, r);

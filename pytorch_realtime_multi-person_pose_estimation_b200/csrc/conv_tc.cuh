@@ -22,7 +22,7 @@ constexpr int kBStageBytes = 128 * 128;                                 // up to
 #endif
 constexpr int kNumBStages = B2P_CONV_B_STAGES;
 constexpr int kNumPatchStages = 2;
-constexpr int kConvTcThreads = 224;   // warps: 0 patch TMA, 1 MMA, 2-5 epilogue, 6 weight TMA
+constexpr int kConvTcThreads = 352;   // warps: 0 patch TMA, 1 MMA, 2-5 and 7-10 epilogue (two per TMEM lane quarter), 6 weight TMA
 constexpr int kConvTcSmemBytes = kNumPatchStages * kPatchBytes + kNumBStages * kBStageBytes + 1024 /*align*/ + 256;
 
 struct ConvTcArgs {
