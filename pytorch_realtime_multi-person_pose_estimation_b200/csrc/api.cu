@@ -247,13 +247,17 @@ int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __n
     a.n_img = n; a.H = H; a.W = W; a.ksize = L.ks; a.cin_blocks = L.cin_blocks;
     a.in_ch_base = in_ch_base; a.in_ch_group_stride = in_group_stride; a.groups = L.groups;
     a.n_tile = L.n_tile; a.n_tiles = L.n_tiles; a.bias = L.bias; a.relu = L.relu; a.pool = L.pool;
+    if (net->plan_split) {     // bf16x3: K-chunked accumulation, one 32-column chunk per epilogue warp, so N <= 64
+        a.chunk = 1;
+        if (L.n_tile > 64) { a.n_tile = 64; a.n_tiles = L.n_tiles * (L.n_tile / 64); }
+    }
     a.out = out; a.out_cstride = out_cstride;
     a.out_ch_off[0] = off0; a.out_ch_off[1] = off1;
     a.store_ch[0] = store0; a.store_ch[1] = store1;
     a.out_f32[0] = f32_0; a.out_f32[1] = f32_1;
     a.f32_ch[0] = f32c0; a.f32_ch[1] = f32c1;
     a.use_base_offset = 0;
-    a.pair = (net->conv_pair && L.n_tile % 32 == 0 && L.n_tile >= 64) ? 1 : 0;    // heads (N = 48) stay single-CTA
+    a.pair = (net->conv_pair && a.n_tile % 32 == 0 && a.n_tile >= 64) ? 1 : 0;    // heads (N = 48) stay single-CTA
     const __nv_bfloat16* in_lo = nullptr;
     if (net->plan_split) {
         a.split = 1;

@@ -69,7 +69,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <bool kPair>
+template <bool kPair, bool kChunk>
 __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     extern __shared__ uint8_t smem_raw[];
     // pair mode: each weight stage holds half of the N rows, so the same bytes give twice the stages
@@ -202,9 +202,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             const uint32_t row_wrap = (kPatchPitch - a.ksize) * 8;     // (16-byte units) jump to the next filter row
             uint32_t pi = 0, pph = 0, bi = 0, bph = 0, ai = 0, aph = 0;
             for (int t = work0; t < total_tiles; t += wstep) {
-                mbar_wait(&acc_empty[ai], aph ^ 1, 3);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + ai * 256;
+                if (!kChunk) {
+                    mbar_wait(&acc_empty[ai], aph ^ 1, 3);
+                    tc_fence_after();
+                }
                 uint32_t accumulate = 0;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
                     for (int term = 0; term < nterms; ++term) {
@@ -214,6 +215,16 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                         uint32_t a_lo = patch_lo0 + pi * (kPatchBytes >> 4);     // window start of tap (0,0), sub-tile 0
                         int dx = 0;
                         for (int tap = 0; tap < taps; ++tap) {
+                            // K-chunked mode: every filter row (7x7) / every (channel block, term) starts a fresh
+                            // accumulator set; the epilogue warps sum the chunks in fp32 registers
+                            const bool c_start = kChunk && (a.ksize == 7 ? dx == 0 : tap == 0);
+                            const bool c_end = kChunk && (a.ksize == 7 ? dx == a.ksize - 1 : tap == taps - 1);
+                            if (c_start) {
+                                mbar_wait(&acc_empty[ai], aph ^ 1, 3);
+                                tc_fence_after();
+                                accumulate = 0;
+                            }
+                            const uint32_t d_tmem = tmem_base + ai * 256;
                             mbar_wait(&b_full[bi], bph, 5);
                             tc_fence_after();
                             const uint32_t b_lo = b_lo0 + bi * (kBStride >> 4);
@@ -230,22 +241,20 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                                                       bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
                                     }
                                 }
+                                const bool tile_end = !kChunk && tap == taps - 1 && cb == a.cin_blocks - 1 && term == nterms - 1;
                                 if (kPair) {
                                     umma_commit_pair(&b_empty[bi]);
-                                    if (tap == taps - 1) {
-                                        if (release_patch) umma_commit_pair(&patch_empty[pi]);
-                                        if (cb == a.cin_blocks - 1 && term == nterms - 1) umma_commit_pair(&acc_full[ai]);
-                                    }
+                                    if (tap == taps - 1 && release_patch) umma_commit_pair(&patch_empty[pi]);
+                                    if (tile_end || c_end) umma_commit_pair(&acc_full[ai]);
                                 } else {
                                     umma_commit(&b_empty[bi]);
-                                    if (tap == taps - 1) {
-                                        if (release_patch) umma_commit(&patch_empty[pi]);
-                                        if (cb == a.cin_blocks - 1 && term == nterms - 1) umma_commit(&acc_full[ai]);
-                                    }
+                                    if (tap == taps - 1 && release_patch) umma_commit(&patch_empty[pi]);
+                                    if (tile_end || c_end) umma_commit(&acc_full[ai]);
                                 }
                             }
                             __syncwarp();
                             accumulate = 1;
+                            if (c_end) { if (++ai == 2) { ai = 0; aph ^= 1; } }
                             if (++bi == kBStages) { bi = 0; bph ^= 1; }
                             a_lo += 8;                                            // next tap: one pixel (128 B) to the right
                             if (++dx == a.ksize) { dx = 0; a_lo += row_wrap; }
@@ -253,7 +262,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                         if (release_patch) { if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; } }
                     }
                 }
-                if (++ai == 2) { ai = 0; aph ^= 1; }
+                if (!kChunk) { if (++ai == 2) { ai = 0; aph ^= 1; } }
             }
         }
     } else if (warp >= 2 && warp != 6) {
@@ -271,6 +280,113 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         uint32_t ai = 0, aph = 0;
         for (int t = work0; t < total_tiles; t += wstep) {
             const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank);
+            if (kChunk) {
+                // ---- K-chunked accumulation (n_tile <= 64: this warp owns ONE 32-column chunk of both sub-tiles) ----
+                float accr[2][32];
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) accr[sub][j] = 0.f;
+                const int c0 = half * 32;
+                const bool mine = c0 < a.n_tile, full = c0 + 32 <= a.n_tile;
+                const int nchunks = a.cin_blocks * nterms * (a.ksize == 7 ? 7 : 1);
+                for (int chk = 0; chk < nchunks; ++chk) {
+                    mbar_wait(&acc_full[ai], aph, 6);
+                    tc_fence_after();
+                    if (mine) {
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ai * 256 + sub * 128 + c0;
+                            uint32_t r[32];
+                            if (full) tmem_ld32(taddr, r);
+                            else {
+                                uint32_t r16[16];
+                                tmem_ld16(taddr, r16);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0; }
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) accr[sub][j] = __fadd_rn(accr[sub][j], __uint_as_float(r[j]));
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (kPair) mbar_arrive_leader(&acc_empty[ai]);
+                        else mbar_arrive(&acc_empty[ai]);
+                    }
+                    if (++ai == 2) { ai = 0; aph ^= 1; }
+                }
+                if (mine) {
+                    const int ch_tile = tc.nt * a.n_tile;
+                    const float* bias = a.bias + (tc.g * a.n_tiles + tc.nt) * a.n_tile;
+                    const int store_ch = a.store_ch[tc.g];
+                    float* of32 = a.out_f32[tc.g];
+                    const int f32_ch = a.f32_ch[tc.g];
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int y = tc.y0 + h_in;
+                        const int x = tc.x0 + sub * 8 + w_in;
+                        const bool valid = tc.valid && (y < a.H) && (x < a.W);
+                        const bool writer = a.pool ? (valid && !(lane & 1) && !(lane & 8)) : valid;
+                        const int yo = a.pool ? y >> 1 : y;
+                        const int xo = a.pool ? x >> 1 : x;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float bj = (full || j < 16) ? __ldg(bias + c0 + j) : 0.f;
+                            v[j] = accr[sub][j] + bj;
+                            if (a.relu) v[j] = fmaxf(v[j], 0.f);
+                        }
+                        if (a.pool) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                                v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 8));
+                            }
+                        }
+                        if (writer) {
+                            if (a.out != nullptr) {
+                                __nv_bfloat16* dst = a.out + (static_cast<size_t>(tc.n * Ho + yo) * Wo + xo) * a.out_cstride +
+                                                     a.out_ch_off[tc.g] + ch_tile + c0;
+#pragma unroll
+                                for (int q8 = 0; q8 < 4; ++q8) {
+                                    if (c0 + 8 * q8 < store_ch) {
+                                        uint4 u = make_uint4(pack_bf16x2(v[8 * q8], v[8 * q8 + 1]), pack_bf16x2(v[8 * q8 + 2], v[8 * q8 + 3]),
+                                                             pack_bf16x2(v[8 * q8 + 4], v[8 * q8 + 5]), pack_bf16x2(v[8 * q8 + 6], v[8 * q8 + 7]));
+                                        *reinterpret_cast<uint4*>(dst + 8 * q8) = u;
+                                    }
+                                }
+                                if (a.out_lo != nullptr) {
+                                    __nv_bfloat16* dlo = a.out_lo + (dst - a.out);
+#pragma unroll
+                                    for (int q8 = 0; q8 < 4; ++q8) {
+                                        if (c0 + 8 * q8 < store_ch) {
+                                            float r8[8];
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j)
+                                                r8[j] = v[8 * q8 + j] - __bfloat162float(__float2bfloat16_rn(v[8 * q8 + j]));
+                                            uint4 u = make_uint4(pack_bf16x2(r8[0], r8[1]), pack_bf16x2(r8[2], r8[3]),
+                                                                 pack_bf16x2(r8[4], r8[5]), pack_bf16x2(r8[6], r8[7]));
+                                            *reinterpret_cast<uint4*>(dlo + 8 * q8) = u;
+                                        }
+                                    }
+                                }
+                            }
+                            if (of32 != nullptr) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const int c = ch_tile + c0 + j;
+                                    if (c < f32_ch)
+                                        of32[(static_cast<size_t>(tc.n * f32_ch + c) * Ho + yo) * Wo + xo] = v[j];
+                                }
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             mbar_wait(&acc_full[ai], aph, 6);
             tc_fence_after();
             const int ch_tile = tc.nt * a.n_tile;                    // first channel of this n-tile within the group
@@ -383,12 +499,23 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
 }
 
 __global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcArgs a) {
-    conv_tc_body<false>(a);
+    conv_tc_body<false, false>(a);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvTcThreads, 1)
     conv_tc_pair_kernel(const __grid_constant__ ConvTcArgs a) {
-    conv_tc_body<true>(a);
+    conv_tc_body<true, false>(a);
+}
+
+// K-chunked accumulation (a.chunk; the high-precision split mode): the tensor core sums only one filter row / one channel
+// block at a time into TMEM, the epilogue warps add the chunks in fp32 registers with round-to-nearest.
+__global__ void __launch_bounds__(kConvTcThreads, 1) conv_tc_chunk_kernel(const __grid_constant__ ConvTcArgs a) {
+    conv_tc_body<false, true>(a);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvTcThreads, 1)
+    conv_tc_pair_chunk_kernel(const __grid_constant__ ConvTcArgs a) {
+    conv_tc_body<true, true>(a);
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -458,21 +585,33 @@ cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream
     if (a.pool && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
     const int tiles_x = (a.W + kTileW - 1) / kTileW;
     const int tiles_y = (a.H + kTileH - 1) / kTileH;
+    static DynSmemOptIn optin_chunk, optin_pair_chunk;
+    if (a.chunk && a.n_tile > 64) return cudaErrorInvalidValue;      // one 32-column chunk per epilogue warp
     if (a.pair) {
-        cudaError_t e = optin_pair.ensure(conv_tc_pair_kernel, kConvTcSmemBytes);
-        if (e != cudaSuccess) return e;
         const int pairs = ((a.n_img * tiles_y * tiles_x + 1) / 2) * a.groups * a.n_tiles;
         const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
-        conv_tc_pair_kernel<<<2 * clusters, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);   // __cluster_dims__(2,1,1)
+        if (a.chunk) {
+            cudaError_t e = optin_pair_chunk.ensure(conv_tc_pair_chunk_kernel, kConvTcSmemBytes);
+            if (e != cudaSuccess) return e;
+            conv_tc_pair_chunk_kernel<<<2 * clusters, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+        } else {
+            cudaError_t e = optin_pair.ensure(conv_tc_pair_kernel, kConvTcSmemBytes);
+            if (e != cudaSuccess) return e;
+            conv_tc_pair_kernel<<<2 * clusters, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);   // __cluster_dims__(2,1,1)
+        }
         return cudaGetLastError();
-    }
-    {
-        cudaError_t e = optin.ensure(conv_tc_kernel, kConvTcSmemBytes);
-        if (e != cudaSuccess) return e;
     }
     const int total = a.n_img * tiles_y * tiles_x * a.groups * a.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
-    conv_tc_kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+    if (a.chunk) {
+        cudaError_t e = optin_chunk.ensure(conv_tc_chunk_kernel, kConvTcSmemBytes);
+        if (e != cudaSuccess) return e;
+        conv_tc_chunk_kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+    } else {
+        cudaError_t e = optin.ensure(conv_tc_kernel, kConvTcSmemBytes);
+        if (e != cudaSuccess) return e;
+        conv_tc_kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+    }
     return cudaGetLastError();
 }
 

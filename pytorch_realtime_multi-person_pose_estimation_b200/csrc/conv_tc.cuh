@@ -51,6 +51,8 @@ struct ConvTcArgs {
     __nv_bfloat16* out_lo;    // residual plane of the output (same geometry as `out`), split mode only
     // ---- CTA-pair mode (tcgen05 cta_group::2): clusters of two CTAs share each weight slice; needs n_tile % 32 == 0
     int pair;
+    // ---- K-chunked accumulation (n_tile <= 64): see conv_tc_chunk_kernel
+    int chunk;
     // ---- tensor maps
     CUtensorMap tm_in;        // 4D (C, W, H, N) bf16, box (64, 24, 16+ks-1, 1), SWIZZLE_128B
     CUtensorMap tm_w;         // 3D (cin_pad, groups*n_tiles*n_tile, 2*taps) bf16 [hi taps | lo taps], box (64, n_tile, 1)

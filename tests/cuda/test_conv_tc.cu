@@ -32,7 +32,7 @@ struct Case {
 };
 
 // head: out_ch_off {0,40}, store {40,24}, f32 {38,19}; cout_g is the padded per-group Cout (n_tile).
-static int run_case(const Case& c, int use_bo, int num_sms, int pair) {
+static int run_case(const Case& c, int use_bo, int num_sms, int pair, int chunk = 0) {
     const int taps = c.ks * c.ks, pad = c.ks / 2;
     const int cin_blocks = c.cin_g / 64;
     const int in_c = (c.in_stride_g == 0) ? c.cin_g : c.cin_g * c.groups;
@@ -88,6 +88,7 @@ static int run_case(const Case& c, int use_bo, int num_sms, int pair) {
     }
     a.use_base_offset = use_bo;
     a.pair = pair;
+    a.chunk = chunk;
     CK(conv_tc_make_maps(a, d_in, in_c, d_w));
     CK(conv_tc_launch(a, num_sms, 0));
     cudaError_t e = cudaDeviceSynchronize();
@@ -161,8 +162,8 @@ static int run_case(const Case& c, int use_bo, int num_sms, int pair) {
                         }
                     }
                 }
-    printf("case %-28s bo=%d pair=%d : max|err| bf16 %.5f  f32 %.6f  (max|ref| %.3f)  bad=%ld  %s\n", c.name, use_bo, pair,
-           max_err, max_err32, max_ref, bad, bad == 0 ? "OK" : "MISMATCH");
+    printf("case %-28s bo=%d pair=%d chunk=%d : max|err| bf16 %.5f  f32 %.3e  (max|ref| %.3f)  bad=%ld  %s\n", c.name, use_bo,
+           pair, chunk, max_err, max_err32, max_ref, bad, bad == 0 ? "OK" : "MISMATCH");
     cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out);
     for (int g = 0; g < 2; ++g) if (d_f32[g]) cudaFree(d_f32[g]);
     return bad == 0 ? 0 : 1;
@@ -238,6 +239,8 @@ int main(int argc, char** argv) {
         {"1x1 512->512 46x46 4 ntiles", 1, 46, 46, 1, 1, 512, 512, 512, 128, 1, 0, 0},
         {"3x3 64->128 odd tiles 3x40x16", 3, 40, 16, 3, 1, 64, 64, 128, 128, 1, 0, 0},     // 3 images x 3 x 1 = 9 pixel tiles (odd)
         {"7x7 2grp 128->128 1x16x16", 1, 16, 16, 7, 2, 128, 128, 128, 128, 1, 0, 0},        // ONE pixel tile: the odd CTA idles
+        {"7x7 2grp 128->128 nt64 30x30", 1, 30, 30, 7, 2, 128, 128, 128, 64, 1, 0, 0},      // two 64-wide n-tiles per group
+        {"7x7 head 128->38|19 K=6272", 2, 46, 46, 7, 2, 128, 128, 48, 48, 0, 0, 1},          // fp32 outputs after a long K loop
     };
     // use_base_offset=0 is the product setting: the UMMA shared-memory descriptor swizzles on absolute smem address
     // bits, so shifted (non-1024B-aligned) window starts need no phase field.  `probe` also runs the =1 variant
@@ -247,12 +250,14 @@ int main(int argc, char** argv) {
     for (int bo = probe ? 1 : 0; bo >= 0; --bo) {
         for (const Case& c : cases) {
             for (int pair = 0; pair <= ((c.n_tile % 32 == 0) ? 1 : 0); ++pair) {     // CTA-pair mode where it is eligible
-                int r = run_case(c, bo, sms, pair);
-                if (r >= 100) {   // sticky CUDA error: the context is gone
-                    printf("aborting after kernel failure\n");
-                    return 3;
+                for (int chunk = 0; chunk <= (c.n_tile <= 64 ? 1 : 0); ++chunk) {    // K-chunked accumulation (N <= 64)
+                    int r = run_case(c, bo, sms, pair, chunk);
+                    if (r >= 100) {   // sticky CUDA error: the context is gone
+                        printf("aborting after kernel failure\n");
+                        return 3;
+                    }
+                    if (bo == 0) fails += r;
                 }
-                if (bo == 0) fails += r;
             }
         }
     }

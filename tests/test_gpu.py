@@ -14,7 +14,8 @@ from oracle import glue_port, net_exact, net_port, nms_port, pafprocess_oracle, 
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-3          # BASELINE.json north_star: heat/PAF within 1e-3 max-abs in fp32 (mode "fp32")
-BF16X3_TOL = 3e-3        # hi+lo bf16 planes on the tensor cores: measured 1.4e-3 @368x368 (floor = TC fp32 accumulation)
+BF16X3_TOL = 1e-3        # the same bar for the tensor-core mode: hi+lo bf16 planes, K-chunked accumulation (measured 1.4e-4
+                         # @368x368; 1.4e-3 when the tensor core accumulates all of K = 6272 by itself)
 BF16_TOL = 0.15          # bf16 operands through 52 conv layers, outputs O(1..4); measured value is printed
 
 
