@@ -153,8 +153,9 @@ def run_ours(args):
         nh = 0
         for k in range(BATCH):
             nh += len(eng.post.humans(k))
-        # what actually crosses PCIe per step: counts/status/n_humans + the full-capacity person buffer
-        d2h_bytes.append(4 * BATCH * (1 + 1 + 18) + BATCH * eng.post.human_cap * 73 * 4)
+        # what actually crosses PCIe per step: counts/status/n_humans + the person rows that exist (the assembly kernel
+        # writes them straight into the pinned host slot)
+        d2h_bytes.append(4 * BATCH * (1 + 1 + 18) + nh * 73 * 4)
         return nh
 
     for i in range(args.warmup):

@@ -247,9 +247,14 @@ int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __n
     a.n_img = n; a.H = H; a.W = W; a.ksize = L.ks; a.cin_blocks = L.cin_blocks;
     a.in_ch_base = in_ch_base; a.in_ch_group_stride = in_group_stride; a.groups = L.groups;
     a.n_tile = L.n_tile; a.n_tiles = L.n_tiles; a.bias = L.bias; a.relu = L.relu; a.pool = L.pool;
+    {   // small batches: a 128-wide layer whose tiles fill less than half of the SMs is split into 64-wide n-tiles (twice
+        // the CTAs, each with half the MMA work; the weight layout does not depend on the n-tile)
+        const int tiles = n * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW) * L.groups * L.n_tiles;
+        if (L.n_tile == 128 && 2 * tiles <= net->num_sms) { a.n_tile = 64; a.n_tiles = L.n_tiles * 2; }
+    }
     if (net->plan_split) {     // bf16x3: K-chunked accumulation, one 32-column chunk per epilogue warp, so N <= 64
         a.chunk = 1;
-        if (L.n_tile > 64) { a.n_tile = 64; a.n_tiles = L.n_tiles * (L.n_tile / 64); }
+        if (a.n_tile > 64) { a.n_tile = 64; a.n_tiles = L.n_tiles * (L.n_tile / 64); }
     }
     a.out = out; a.out_cstride = out_cstride;
     a.out_ch_off[0] = off0; a.out_ch_off[1] = off1;
@@ -692,7 +697,7 @@ int b200pose_post_create(b200pose_post** out, int cuda_device, int batch_cap, in
         CU(cudaHostAlloc(&p->hp_nh[b], (size_t)batch_cap * sizeof(int), cudaHostAllocDefault));
         CU(cudaHostAlloc(&p->hp_status[b], (size_t)batch_cap * sizeof(int), cudaHostAllocDefault));
         CU(cudaHostAlloc(&p->hp_counts[b], (size_t)batch_cap * 18 * sizeof(int), cudaHostAllocDefault));
-        CU(cudaHostAlloc(&p->hp_humans[b], (size_t)batch_cap * human_cap * kHumanFloats * sizeof(float), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&p->hp_humans[b], (size_t)batch_cap * human_cap * kHumanFloats * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));   // written by assemble_kernel (same pointer on the device: unified addressing)
         CU(cudaEventCreateWithFlags(&p->ev_ld[b], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&p->ev_maps, cudaEventDisableTiming));
@@ -729,17 +734,18 @@ void b200pose_post_destroy(b200pose_post* p) {
 static int enqueue_assemble_and_fetch(b200pose_post* p, int n, cudaStream_t st) {
     CU(cudaEventRecord(p->ev_limbs, st));
     CU(cudaStreamWaitEvent(p->s2, p->ev_limbs, 0));
+    const int b = (int)(p->runs & 1);
+    // the assembly kernel writes the person rows straight into this run's pinned host slot (unified addressing): only the
+    // rows that exist cross PCIe, instead of a copy of the full-capacity buffer (4.8 MB per step at batch 32)
+    p->pb.humans_out = p->hp_humans[b];
     cudaError_t e = post_assemble(p->pb, n, p->s2);
     if (e != cudaSuccess) return fail("post_assemble: %s", cudaGetErrorString(e));
     ++g_launches;
     CU(cudaEventRecord(p->ev_asm, p->s2));
-    const int b = (int)(p->runs & 1);
     const PostBuffers& pb = p->pb;
     CU(cudaMemcpyAsync(p->hp_nh[b], pb.n_humans, n * sizeof(int), cudaMemcpyDeviceToHost, p->s2));
     CU(cudaMemcpyAsync(p->hp_status[b], pb.status, n * sizeof(int), cudaMemcpyDeviceToHost, p->s2));
     CU(cudaMemcpyAsync(p->hp_counts[b], pb.counts, (size_t)n * 18 * sizeof(int), cudaMemcpyDeviceToHost, p->s2));
-    CU(cudaMemcpyAsync(p->hp_humans[b], pb.humans, (size_t)n * pb.human_cap * kHumanFloats * sizeof(float),
-                       cudaMemcpyDeviceToHost, p->s2));
     CU(cudaEventRecord(p->ev_fetch[b], p->s2));
     p->slot_n[b] = n;
     p->runs += 1;

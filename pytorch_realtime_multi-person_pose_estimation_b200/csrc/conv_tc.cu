@@ -580,6 +580,17 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
     return cudaSuccess;
 }
 
+namespace {
+// (Programmatic dependent launch of consecutive layers was measured and rejected: the isolated network gains ~1 %, the
+// whole step loses ~2 % at batch 32 - 3214 vs 3297 frames/s - because the next layer's CTAs then win every freed SM
+// against the post-processing kernels of the previous batch; profiles/r02_ab_pdl.txt.)
+template <class Kernel>
+cudaError_t launch_plain(Kernel kernel, int grid, cudaStream_t stream, const ConvTcArgs& a) {
+    kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+    return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream) {
     static DynSmemOptIn optin, optin_pair;   // per device: a second net on another GPU of the same process needs its own opt-in
     if (a.pool && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
@@ -593,26 +604,23 @@ cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream
         if (a.chunk) {
             cudaError_t e = optin_pair_chunk.ensure(conv_tc_pair_chunk_kernel, kConvTcSmemBytes);
             if (e != cudaSuccess) return e;
-            conv_tc_pair_chunk_kernel<<<2 * clusters, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+            return launch_plain(conv_tc_pair_chunk_kernel, 2 * clusters, stream, a);
         } else {
             cudaError_t e = optin_pair.ensure(conv_tc_pair_kernel, kConvTcSmemBytes);
             if (e != cudaSuccess) return e;
-            conv_tc_pair_kernel<<<2 * clusters, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);   // __cluster_dims__(2,1,1)
+            return launch_plain(conv_tc_pair_kernel, 2 * clusters, stream, a);   // __cluster_dims__(2,1,1)
         }
-        return cudaGetLastError();
     }
     const int total = a.n_img * tiles_y * tiles_x * a.groups * a.n_tiles;
     const int grid = total < num_sms ? total : num_sms;
     if (a.chunk) {
         cudaError_t e = optin_chunk.ensure(conv_tc_chunk_kernel, kConvTcSmemBytes);
         if (e != cudaSuccess) return e;
-        conv_tc_chunk_kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
-    } else {
-        cudaError_t e = optin.ensure(conv_tc_kernel, kConvTcSmemBytes);
-        if (e != cudaSuccess) return e;
-        conv_tc_kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
+        return launch_plain(conv_tc_chunk_kernel, grid, stream, a);
     }
-    return cudaGetLastError();
+    cudaError_t e = optin.ensure(conv_tc_kernel, kConvTcSmemBytes);
+    if (e != cudaSuccess) return e;
+    return launch_plain(conv_tc_kernel, grid, stream, a);
 }
 
 }  // namespace b2p

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(PostBuffers pb) {
     }
     __syncthreads();
     const int nh = s_nh;
-    float* out = pb.humans + (long)img * pb.human_cap * kHumanFloats;
+    float* out = (pb.humans_out ? pb.humans_out : pb.humans) + (long)img * pb.human_cap * kHumanFloats;
     for (int e = tid; e < nh * kHumanFloats; e += kAsmThreads) {
         const int hi = e / kHumanFloats, f = e - hi * kHumanFloats;
         const float* row = rows + sm_kept[hi] * kRowFloats;

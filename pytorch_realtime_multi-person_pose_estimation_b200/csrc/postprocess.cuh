@@ -64,6 +64,9 @@ struct PostBuffers {
     // results
     int* n_humans;      // [B]
     float* humans;      // [B][human_cap][1 + 18*4]: score, then per part (x, y, peak score, cid or -1)
+    float* humans_out;  // where assemble_kernel writes the rows: `humans`, or (set per run) a pinned HOST buffer of the same
+                        // geometry - the kernel then exports exactly the used rows over PCIe and no copy of the full-capacity
+                        // buffer follows
     unsigned long long* dbg;   // [16] diagnostics: max cycles per limbs_kernel phase, candidate counts
     int* status_acc;    // [B] OR of `status` over every run since the last reset (b200pose_post_status_accum)
     int* status;        // [B] bit0 peak overflow, bit1 candidate pool overflow, bit2 row overflow, bit3 human overflow,
