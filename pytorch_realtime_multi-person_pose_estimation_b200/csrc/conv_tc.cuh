@@ -16,9 +16,10 @@ constexpr int kMaxKs = 7;
 constexpr int kPatchBytes = kPatchPitch * (kTileH + kMaxKs - 1) * 128;  // 67,584 B per 64-channel block
 constexpr int kBStageBytes = 128 * 128;                                 // up to N=128 rows of 64 bf16
 #ifndef B2P_CONV_B_STAGES
-#define B2P_CONV_B_STAGES 3      // weight (B operand) pipeline depth: 3, 4 and 5 stages measure the same on B200 (2245 / 2246 /
-                                 // 2249 frames/s, profiles/r02_variants.txt); 3 leaves 42 KB of the SM's shared memory to
-                                 // the post-processing kernels of the previous batch that run next to the convolutions
+#define B2P_CONV_B_STAGES 2      // weight (B operand) ring: 2 x 16 KB stages, i.e. FOUR 8 KB half-slices in CTA-pair mode.  The
+                                 // shared memory a conv CTA leaves free decides which post-processing kernels of the previous
+                                 // batch can run NEXT to it: with 3 stages (185 KB) the small ones fit, taking everything (four
+                                 // patch stages, 230 KB) cost 9 % of the step (3 254 -> 2 947 frames/s); see DESIGN.md 2.4
 #endif
 constexpr int kNumBStages = B2P_CONV_B_STAGES;
 constexpr int kNumPatchStages = 2;
