@@ -122,7 +122,9 @@ def run_ours(args):
     # enough rotating device batches that one full rotation exceeds the 126 MB L2 (10 at batch 32)
     n_rot = max(10, -(-130_000_000 // (BATCH * SH * SW * 3)))
     devin = [torch.randint(0, 256, (BATCH, SH, SW, 3), generator=g, dtype=torch.uint8).to(dev) for i in range(n_rot)]
-    stream = torch.cuda.current_stream()
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)      # a real stream (not the legacy default): the forward pass replays as a CUDA graph
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
 
     def barrier():

@@ -151,6 +151,23 @@ struct b200pose_net {
     };
     bool plan_cache_on = true;
     bool conv_pair = true;            // tcgen05 cta_group::2 CTA pairs for the N >= 64 layers (B200POSE_CONV_PAIR=0: single CTAs)
+    // The 52 launches of a forward pass are captured once per (shape, mode, input pointer) into a CUDA graph and replayed
+    // (B200POSE_GRAPH=0: plain launches).  Graphs embed the tensor maps, i.e. buffer addresses: every plan build drops them.
+    // Capture needs a real stream: calls on the legacy default stream (0) launch directly.
+    struct GraphKey {
+        int n, H, W, mode, in_u8;
+        const void* in;
+        bool operator<(const GraphKey& o) const {
+            if (n != o.n) return n < o.n;
+            if (H != o.H) return H < o.H;
+            if (W != o.W) return W < o.W;
+            if (mode != o.mode) return mode < o.mode;
+            if (in_u8 != o.in_u8) return in_u8 < o.in_u8;
+            return in < o.in;
+        }
+    };
+    bool use_graph = true;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
     int kn = 0, kH = 0, kW = 0, kmode = -1;      // key of the plan currently held in `plan`
     std::vector<PlanEntry> plan_cache;
     DevBuf<__nv_bfloat16> t1, t2, t3, t4, t5a, t5b, t6, t7, t8, t9, cat, bra, brb, br512;
@@ -379,22 +396,53 @@ bool plan_cache_swap(b200pose_net* net, int n, int H, int W, int want) {
     return false;
 }
 
+void drop_graphs(b200pose_net* net) {
+    for (auto& kv : net->graphs) cudaGraphExecDestroy(kv.second);
+    net->graphs.clear();
+}
+
+int launch_forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, int W, cudaStream_t st, bool split) {
+    CU(conv_first_launch(d_in, in_u8, net->d_w[0], net->d_b[0], net->t1.p, split ? net->l1.p : nullptr, n, H, W, st));
+    for (const ConvTcArgs& a : net->plan) CU(conv_tc_launch(a, net->num_sms, st));
+    return 0;
+}
+
 int forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, int W, cudaStream_t st, bool split) {
     const int want = split ? B200POSE_MODE_BF16X3 : B200POSE_MODE_BF16;
     if (net->pn != n || net->pH != H || net->pW != W || net->pmode != want) {
         if (!(net->plan_cache_on && plan_cache_swap(net, n, H, W, want))) {
             CU(cudaStreamSynchronize(st));
+            drop_graphs(net);                   // the buffers the captured tensor maps point into may move
             if (build_plan_bf16(net, n, H, W, split, st)) return 1;
             net->kn = n; net->kH = H; net->kW = W; net->kmode = want;
         }
         net->pn = n; net->pH = H; net->pW = W; net->pmode = want;
     }
-    CU(conv_first_launch(d_in, in_u8, net->d_w[0], net->d_b[0], net->t1.p, split ? net->l1.p : nullptr, n, H, W, st));
-    ++g_launches;
-    for (const ConvTcArgs& a : net->plan) {
-        CU(conv_tc_launch(a, net->num_sms, st));
-        ++g_launches;
+    const long launches = 1 + (long)net->plan.size();
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (net->use_graph && st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+        const b200pose_net::GraphKey key{n, H, W, want, in_u8, d_in};
+        auto it = net->graphs.find(key);
+        if (it == net->graphs.end()) {
+            if (net->graphs.size() >= 64) drop_graphs(net);
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = launch_forward_bf16(net, d_in, in_u8, n, H, W, st, split);
+            const cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+            const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+            it = net->graphs.emplace(key, exec).first;
+        }
+        CU(cudaGraphLaunch(it->second, st));
+        g_launches += launches;
+        return 0;
     }
+    if (launch_forward_bf16(net, d_in, in_u8, n, H, W, st, split)) return 1;
+    g_launches += launches;
     return 0;
 }
 
@@ -497,6 +545,8 @@ int b200pose_net_create(b200pose_net** out, int cuda_device) {
     net->plan_cache_on = !(pc && pc[0] == '0');
     const char* cp = getenv("B200POSE_CONV_PAIR");
     net->conv_pair = !(cp && cp[0] == '0');
+    const char* gr = getenv("B200POSE_GRAPH");
+    net->use_graph = !(gr && gr[0] == '0');
     *out = net;
     return 0;
 }
@@ -504,6 +554,7 @@ int b200pose_net_create(b200pose_net** out, int cuda_device) {
 void b200pose_net_destroy(b200pose_net* net) {
     if (!net) return;
     cudaSetDevice(net->device);
+    drop_graphs(net);
     for (int i = 0; i < kNumConvs; ++i) { if (net->d_w[i]) cudaFree(net->d_w[i]); if (net->d_b[i]) cudaFree(net->d_b[i]); }
     for (TcLayer& L : net->tc) { if (L.w) cudaFree(L.w); if (L.bias) cudaFree(L.bias); }
     DevBuf<__nv_bfloat16>* bb[] = {&net->t1, &net->t2, &net->t3, &net->t4, &net->t5a, &net->t5b, &net->t6,
@@ -569,6 +620,7 @@ int b200pose_net_finalize(b200pose_net* net) {
         }
     net->pn = net->pH = net->pW = 0;
     net->pmode = -1;
+    drop_graphs(net);
     net->plan_cache.clear();      // cached plans point at the previous packed weights
     net->plan.clear(); net->plan_flops.clear();
     net->kmode = -1;

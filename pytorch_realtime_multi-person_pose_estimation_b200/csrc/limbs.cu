@@ -41,7 +41,10 @@ constexpr int kSubPairs = 256;
 constexpr int kSubPerChunk = kChunkPairs / kSubPairs;
 static_assert(kSubPerChunk * 32 == kScoreThreads, "one warp per sub-chunk");
 
-constexpr int kGatherThreads = 512, kGatherWarps = kGatherThreads / 32;
+#ifndef B2P_GATHER_THREADS
+#define B2P_GATHER_THREADS 512
+#endif
+constexpr int kGatherThreads = B2P_GATHER_THREADS, kGatherWarps = kGatherThreads / 32;
 constexpr int kS = kLimbSmemRange;             // keys per shared-memory range
 constexpr int kSortThreads = 512, kSortWarps = kSortThreads / 32;
 constexpr int kGreedyThreads = 512, kGreedySeg = 2048, kGreedyPer = kGreedySeg / kGreedyThreads;
@@ -249,12 +252,13 @@ __global__ void __launch_bounds__(kScoreThreads) limb_score_kernel(PostBuffers p
 // Rank formulation of libstdc++'s __unguarded_partition_pivot (post_core.h), evaluated row-wise by the whole block:
 // every warp owns a contiguous segment of rows, lanes take consecutive keys, ranks come from ballots + running counts.
 struct PartShared {
-    unsigned long long scan2[kGatherWarps];
+    unsigned long long scan2[16];
     int ksum;
 };
-template <class PosT>
+template <class PosT, int kThreads>
 __device__ int block_rank_partition(unsigned long long* v, int f, int l, PosT* tabA, PosT* tabB, PartShared& sh,
                                     uint32_t* bal = nullptr /* optional cache of 2 x rows stop-flag ballots */) {
+    constexpr int kWarps = kThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u, gt = ~lt & ~(1u << lane);
     if (tid == 0) {       // __move_median_to_first(first, first+1, mid, last-1)
@@ -269,7 +273,7 @@ __device__ int block_rank_partition(unsigned long long* v, int f, int l, PosT* t
     const uint32_t pivot = (uint32_t)(v[f] >> 32);
     const int base = f + 1;
     const int rows = (l - base + 31) >> 5;
-    const int rpw = (rows + kGatherWarps - 1) / kGatherWarps;
+    const int rpw = (rows + kWarps - 1) / kWarps;
     const int r0 = min(rows, wq * rpw), r1 = min(rows, r0 + rpw);
     int cA = 0, cB = 0;
     for (int r = r0; r < r1; ++r) {
@@ -285,7 +289,7 @@ __device__ int block_rank_partition(unsigned long long* v, int f, int l, PosT* t
     __syncthreads();
     unsigned long long pre = 0, tot = 0;
 #pragma unroll
-    for (int k = 0; k < kGatherWarps; ++k) {
+    for (int k = 0; k < kWarps; ++k) {
         const unsigned long long c = sh.scan2[k];
         if (k < wq) pre += c;
         tot += c;
@@ -311,13 +315,13 @@ __device__ int block_rank_partition(unsigned long long* v, int f, int l, PosT* t
     __syncthreads();
     const int lim = totA < totB ? totA : totB;
     int c = 0;
-    for (int k = 1 + tid; k <= lim; k += kGatherThreads) c += (tabA[k] < tabB[k]);
+    for (int k = 1 + tid; k <= lim; k += kThreads) c += (tabA[k] < tabB[k]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0 && c) atomicAdd(&sh.ksum, c);
     __syncthreads();
     const int K = sh.ksum;
-    for (int k = 1 + tid; k <= K; k += kGatherThreads) {
+    for (int k = 1 + tid; k <= K; k += kThreads) {
         const int ia = f + (int)tabA[k], ib = f + (int)tabB[k];
         const unsigned long long t = v[ia]; v[ia] = v[ib]; v[ib] = t;
     }
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(kGatherThreads) limb_gather_kernel(PostBuffers
         } else if (d == 0) {
             if (tid == 0) seq_heap_sort(reinterpret_cast<uint64_t*>(keys), f, l);     // depth limit: std::__partial_sort
         } else {
-            const int cut = block_rank_partition<int32_t>(keys, f, l, gA, gB, s_part,
+            const int cut = block_rank_partition<int32_t, kGatherThreads>(keys, f, l, gA, gB, s_part,
                                                           (l - f - 1 + 31) / 32 <= kBalRows ? s_bal : nullptr);
             if (tid == 0) {
                 int q = g_top;
@@ -611,7 +615,7 @@ __device__ void smem_level_sort(SortSmem& S, int n, int depth) {
         // segments too long for one warp: the whole block, one after the other (only the first levels have any)
         for (int i = 0; i < nbig; ++i) {
             const Seg sg = S.bigs[cur][i];
-            const int cut = block_rank_partition<uint16_t>(S.keys, sg.f, sg.l, S.tabA + sg.f, S.tabB + sg.f, S.part);
+            const int cut = block_rank_partition<uint16_t, kSortThreads>(S.keys, sg.f, sg.l, S.tabA + sg.f, S.tabB + sg.f, S.part);
             if (tid == 0) {
                 push_segment(S, sg.f, cut, sg.d - 1, nx);
                 push_segment(S, cut, sg.l, sg.d - 1, nx);

@@ -30,7 +30,10 @@ __device__ constexpr float k_cubic[8][4] = {
     {-0x1.518p-5f, 0x1.fba8p-1f, 0x1.ad8p-5f, -0x1.68p-9f},   {-0x1.7c4p-4f, 0x1.dbb8p-1f, 0x1.7b2p-3f, -0x1.5fp-6f},
     {-0x1.c5cp-4f, 0x1.a308p-1f, 0x1.5efp-2f, -0x1.9c8p-5f},  {-0x1.a94p-4f, 0x1.5918p-1f, 0x1.0568p-1f, -0x1.4acp-4f}};
 
-constexpr int kPeakThreads = 256;
+#ifndef B2P_PEAK_THREADS
+#define B2P_PEAK_THREADS 256
+#endif
+constexpr int kPeakThreads = B2P_PEAK_THREADS;
 constexpr int kAsmThreads = 128;
 constexpr int kHorStride = 40;   // (2*2+1) * 8
 
@@ -96,7 +99,7 @@ __device__ __forceinline__ void refine_interior_slots(const float* plane, int w,
     }
 }
 
-__global__ void __launch_bounds__(kPeakThreads, 2) peaks_kernel(PostBuffers pb, const float* __restrict__ heat, long h_img,
+__global__ void __launch_bounds__(kPeakThreads, 512 / kPeakThreads) peaks_kernel(PostBuffers pb, const float* __restrict__ heat, long h_img,
                                                              long h_ch, long h_y, long h_x, int h, int w, float thresh) {
     extern __shared__ float sm_f[];
     float* plane = sm_f;                       // [h*w]

@@ -20,6 +20,10 @@ VARIANTS = {
     "range2048": ["-DB2P_LIMB_SMEM_RANGE=2048"],    # sort ranges of 2048 keys: 26 KB of shared memory, fits next to a conv CTA
     "lane32": ["-DB2P_LANE_SORT_KEYS=32"],          # one-lane partitions only below 33 keys
     "lane128": ["-DB2P_LANE_SORT_KEYS=128"],
+    "peaks128": ["-DB2P_PEAK_THREADS=128"],         # 128-thread peak blocks (16 K registers: fit next to a conv CTA)
+    "bstages3": ["-DB2P_CONV_B_STAGES=3"],
+    "gather256": ["-DB2P_GATHER_THREADS=256"],      # 256-thread gather blocks (16 K registers)
+    "fit": ["-DB2P_GATHER_THREADS=256", "-DB2P_PEAK_THREADS=128"],
 }
 
 
