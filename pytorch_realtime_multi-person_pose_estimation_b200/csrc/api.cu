@@ -150,6 +150,8 @@ struct b200pose_net {
         std::vector<const void*> buffers;
     };
     bool plan_cache_on = true;
+    bool conv_pdl = true;             // programmatic dependent launch between the layers of small-batch plans (B200POSE_CONV_PDL=0: never)
+    bool conv_narrow = true;          // 8 x 16 pixel tiles for layers that fill less than half of the SMs (B200POSE_CONV_NARROW=0: never)
     bool conv_pair = true;            // tcgen05 cta_group::2 CTA pairs for the N >= 64 layers (B200POSE_CONV_PAIR=0: single CTAs)
     // The 52 launches of a forward pass are captured once per (shape, mode, input pointer) into a CUDA graph and replayed
     // (B200POSE_GRAPH=0: plain launches).  Graphs embed the tensor maps, i.e. buffer addresses: every plan build drops them.
@@ -264,10 +266,18 @@ int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __n
     a.n_img = n; a.H = H; a.W = W; a.ksize = L.ks; a.cin_blocks = L.cin_blocks;
     a.in_ch_base = in_ch_base; a.in_ch_group_stride = in_group_stride; a.groups = L.groups;
     a.n_tile = L.n_tile; a.n_tiles = L.n_tiles; a.bias = L.bias; a.relu = L.relu; a.pool = L.pool;
-    {   // small batches: a 128-wide layer whose tiles fill less than half of the SMs is split into 64-wide n-tiles (twice
-        // the CTAs, each with half the MMA work; the weight layout does not depend on the n-tile)
-        const int tiles = n * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW) * L.groups * L.n_tiles;
-        if (L.n_tile == 128 && 2 * tiles <= net->num_sms) { a.n_tile = 64; a.n_tiles = L.n_tiles * 2; }
+    {   // small batches: while the layer's CTAs fill less than half of the SMs, halve the work per CTA - 128-wide n-tiles
+        // become 64-wide, then the 16 x 16 pixel tile becomes 8 x 16 (one UMMA sub-tile), then 64-wide n-tiles become
+        // 32-wide (the weight layout does not depend on the n-tile).  B200POSE_CONV_NARROW=0 keeps the 16 x 16 tiles.
+        auto ctas = [&](int narrow, int n_tiles) {
+            const int pix = n * ((H + kTileH - 1) / kTileH) * ((W + (narrow ? 8 : kTileW) - 1) / (narrow ? 8 : kTileW));
+            return (net->conv_pair ? (pix + 1) / 2 * 2 : pix) * L.groups * n_tiles;
+        };
+        if (L.n_tile == 128 && 2 * ctas(0, a.n_tiles) <= net->num_sms) { a.n_tile = 64; a.n_tiles = L.n_tiles * 2; }
+        if (net->conv_narrow && 2 * ctas(0, a.n_tiles) <= net->num_sms) {
+            a.narrow = 1;
+            if (a.n_tile == 64 && net->conv_pair && 2 * ctas(1, a.n_tiles) <= net->num_sms) { a.n_tile = 32; a.n_tiles *= 2; }
+        }
     }
     if (net->plan_split) {     // bf16x3: K-chunked accumulation, one 32-column chunk per epilogue warp, so N <= 64
         a.chunk = 1;
@@ -279,7 +289,11 @@ int add_plan(b200pose_net* net, const TcLayer& L, int n, int H, int W, const __n
     a.out_f32[0] = f32_0; a.out_f32[1] = f32_1;
     a.f32_ch[0] = f32c0; a.f32_ch[1] = f32c1;
     a.use_base_offset = 0;
-    a.pair = (net->conv_pair && a.n_tile % 32 == 0 && a.n_tile >= 64) ? 1 : 0;    // heads (N = 48) stay single-CTA
+    a.pair = (net->conv_pair && a.n_tile % 32 == 0) ? 1 : 0;    // heads (N = 48) stay single-CTA
+    // small batches (the 46 x 46 layers fill less than half of the SMs with 16 x 16 tiles): chain the layers with programmatic
+    // dependent launches; the first tensor-core layer follows conv1_1, which does not signal
+    a.pdl = (net->conv_pdl && !net->plan.empty() &&
+             2 * n * ((H / 8 + kTileH - 1) / kTileH) * ((W / 8 + kTileW - 1) / kTileW) * 2 <= net->num_sms) ? 1 : 0;
     const __nv_bfloat16* in_lo = nullptr;
     if (net->plan_split) {
         a.split = 1;
@@ -429,12 +443,18 @@ int forward_bf16(b200pose_net* net, const void* d_in, int in_u8, int n, int H, i
             cudaGraphExec_t exec = nullptr;
             CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             const int rc = launch_forward_bf16(net, d_in, in_u8, n, H, W, st, split);
-            const cudaError_t e = cudaStreamEndCapture(st, &graph);
-            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (e != cudaSuccess) return fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-            const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e2 != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (rc == 0 && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != 0 || e != cudaSuccess) {      // no graph (e.g. a launch attribute the capture refuses): plain launches from now on
+                cudaGetLastError();
+                fprintf(stderr, "[b200pose] CUDA graph capture of the forward pass failed (%s): launching directly\n",
+                        rc ? b200pose_last_error() : cudaGetErrorString(e));
+                net->use_graph = false;
+                if (launch_forward_bf16(net, d_in, in_u8, n, H, W, st, split)) return 1;
+                g_launches += launches;
+                return 0;
+            }
             it = net->graphs.emplace(key, exec).first;
         }
         CU(cudaGraphLaunch(it->second, st));
@@ -545,6 +565,10 @@ int b200pose_net_create(b200pose_net** out, int cuda_device) {
     net->plan_cache_on = !(pc && pc[0] == '0');
     const char* cp = getenv("B200POSE_CONV_PAIR");
     net->conv_pair = !(cp && cp[0] == '0');
+    const char* nw = getenv("B200POSE_CONV_NARROW");
+    net->conv_narrow = !(nw && nw[0] == '0');
+    const char* pd = getenv("B200POSE_CONV_PDL");
+    net->conv_pdl = !(pd && pd[0] == '0');
     const char* gr = getenv("B200POSE_GRAPH");
     net->use_graph = !(gr && gr[0] == '0');
     *out = net;

@@ -33,6 +33,13 @@
 
 namespace b2p {
 
+#ifdef B2P_CONV_TIMELINE
+__device__ unsigned long long g_conv_timeline[64 * kTlSlots];
+#define B2P_TL(slot) do { if (blockIdx.x < 64) g_conv_timeline[blockIdx.x * kTlSlots + (slot)] = clock64(); } while (0)
+#else
+#define B2P_TL(slot) do { } while (0)
+#endif
+
 namespace {
 
 struct TileCoord {
@@ -45,7 +52,7 @@ struct TileCoord {
 // running at the same time read the same activation patches from L2.
 template <bool kPair>
 __device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int groups, int tiles_x, int tiles_y, int n_img,
-                                                 int rank) {
+                                                 int rank, int tile_w) {
     TileCoord c;
     c.nt = t % n_tiles;
     t /= n_tiles;
@@ -57,7 +64,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int n_tiles, int groups,
         t = 2 * t + rank;
         if (t >= pix_tiles) { t = pix_tiles; c.valid = false; }     // -> n = n_img: TMA zero-fills, nothing is stored
     }
-    c.x0 = (t % tiles_x) * kTileW;
+    c.x0 = (t % tiles_x) * tile_w;
     t /= tiles_x;
     c.y0 = (t % tiles_y) * kTileH;
     c.n = t / tiles_y;
@@ -72,9 +79,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 template <bool kPair, bool kChunk>
 __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     extern __shared__ uint8_t smem_raw[];
-    // pair mode: each weight stage holds half of the N rows, so the same bytes give twice the stages
-    constexpr int kBStages = kPair ? 2 * kNumBStages : kNumBStages;
-    constexpr int kBStride = kPair ? kBStageBytes / 2 : kBStageBytes;
     // SWIZZLE_128B operands need 1024 B alignment.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* patch_smem = smem;
@@ -82,16 +86,20 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + kNumBStages * kBStageBytes);
     uint64_t* patch_full = bars;                          // [2]
     uint64_t* patch_empty = bars + kNumPatchStages;       // [2]
-    uint64_t* b_full = bars + 2 * kNumPatchStages;        // [kBStages]
-    uint64_t* b_empty = b_full + kBStages;                // [kBStages]
-    uint64_t* acc_full = b_empty + kBStages;              // [2]
+    uint64_t* b_full = bars + 2 * kNumPatchStages;        // [kMaxBStages]
+    uint64_t* b_empty = b_full + kMaxBStages;             // [kMaxBStages]
+    uint64_t* acc_full = b_empty + kMaxBStages;           // [2]
     uint64_t* acc_empty = acc_full + 2;                   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    const int tiles_x = (a.W + kTileW - 1) / kTileW;
+    // narrow mode (small batches): the CTA tile is ONE 8 x 16 sub-tile - twice the CTAs, half the MMA work each; the patch
+    // box keeps its 24-pixel pitch (the right part is loaded and not read)
+    const int nsub = a.narrow ? 1 : 2;
+    const int tile_w = 8 * nsub;
+    const int tiles_x = (a.W + tile_w - 1) / tile_w;
     const int tiles_y = (a.H + kTileH - 1) / kTileH;
     const int rank = kPair ? (int)cluster_ctarank() : 0;
     // work items of this CTA (pair mode: of this pair): first, stride, total
@@ -104,6 +112,13 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     const uint32_t patch_tx = kPatchPitch * (kTileH + a.ksize - 1) * 128;
     const int b_rows = kPair ? a.n_tile / 2 : a.n_tile;      // weight rows this CTA loads per tap
     const uint32_t b_tx = b_rows * 128;
+    // The weight ring is cut into stages of `tps` consecutive taps (a.tps, chosen with the tensor map's box): per stage the
+    // producer pays a barrier wait + expect_tx + TMA issue and the MMA warp a barrier wait + elect + commit - about 360 clk,
+    // which bounded the small-batch plans (64 clk of tensor work per tap with 32-wide n-tiles; timeline build, batch 1).
+    const int tps = a.tps;
+    const uint32_t b_stride = b_tx * tps;                    // multiples of 1024 B (n_tile % 16 == 0; pair: n_tile % 32 == 0)
+    const uint32_t nb_fit = (kNumBStages * kBStageBytes) / b_stride;
+    const uint32_t nb = nb_fit < (uint32_t)kMaxBStages ? nb_fit : (uint32_t)kMaxBStages;
     const int nterms = a.split ? 3 : 1;   // split mode: A_hi*W_hi, A_hi*W_lo, A_lo*W_hi per K block
 
     if (warp == 0 && lane == 0) {
@@ -117,7 +132,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                 mbar_init(&patch_full[i], 1);
                 mbar_init(&patch_empty[i], 1);
             }
-            for (int i = 0; i < kBStages; ++i) {
+            for (uint32_t i = 0; i < nb; ++i) {
                 mbar_init(&b_full[i], 1);
                 mbar_init(&b_empty[i], 1);
             }
@@ -136,13 +151,18 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) B2P_TL(1);
+    // PDL (no-ops unless the launch carries the attribute): let the next layer start its prologue now; everything that reads
+    // or writes activations first waits for the previous layer's grid to complete (weights / bias are constants).
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // =========================== TMA producer: activation halo patches ===========================
         if (lane == 0) {
+            pdl_wait();
             uint32_t pi = 0, pph = 0;
             for (int t = work0; t < total_tiles; t += wstep) {
-                const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank);
+                const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank, tile_w);
                 const int ch0 = a.in_ch_base + tc.g * a.in_ch_group_stride;
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
                     for (int plane = 0; plane <= a.split; ++plane) {     // hi plane, then (split mode) the residual plane
@@ -166,21 +186,21 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         if (lane == 0) {
             uint32_t bi = 0, bph = 0;
             for (int t = work0; t < total_tiles; t += wstep) {
-                const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank);
+                const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank, tile_w);
                 const int wrow = (tc.g * a.n_tiles + tc.nt) * a.n_tile + rank * b_rows;   // pair: this CTA's half of N
                 for (int cb = 0; cb < a.cin_blocks; ++cb) {
                     for (int term = 0; term < nterms; ++term) {          // W_hi, (split) W_lo, W_hi
                         const int wsel = (term == 1) ? taps : 0;
-                        for (int tap = 0; tap < taps; ++tap) {
-                            mbar_wait(&b_empty[bi], bph ^ 1, 2);
+                        for (int tap0 = 0; tap0 < taps; tap0 += tps) {       // (the last box of a block may run past `taps`:
+                            mbar_wait(&b_empty[bi], bph ^ 1, 2);             //  those slices are loaded and not read)
                             if (kPair) {
-                                if (rank == 0) mbar_expect_tx(&b_full[bi], 2 * b_tx);
-                                tma_load_3d_pair(b_smem + bi * kBStride, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap);
+                                if (rank == 0) mbar_expect_tx(&b_full[bi], 2 * b_stride);
+                                tma_load_3d_pair(b_smem + bi * b_stride, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap0);
                             } else {
-                                mbar_expect_tx(&b_full[bi], b_tx);
-                                tma_load_3d(b_smem + bi * kBStride, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap);
+                                mbar_expect_tx(&b_full[bi], b_stride);
+                                tma_load_3d(b_smem + bi * b_stride, &a.tm_w, &b_full[bi], cb * 64, wrow, wsel + tap0);
                             }
-                            if (++bi == kBStages) { bi = 0; bph ^= 1; }
+                            if (++bi == nb) { bi = 0; bph ^= 1; }
                         }
                     }
                 }
@@ -199,7 +219,11 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             const uint64_t bdesc_hi = make_sdesc_sw128(0, 1024, 0);
             const uint32_t patch_lo0 = (smem_u32(patch_smem) & 0x3FFFFu) >> 4;
             const uint32_t b_lo0 = (smem_u32(b_smem) & 0x3FFFFu) >> 4;
-            const uint32_t row_wrap = (kPatchPitch - a.ksize) * 8;     // (16-byte units) jump to the next filter row
+            const uint32_t b_tap_step = b_tx >> 4;                      // one tap's slice within a stage
+            const uint32_t b_stage_step = b_stride >> 4;
+            const uint32_t row_wrap = (kPatchPitch - a.ksize) * 8;      // (16-byte units) jump to the next filter row
+            const bool row_chunks = kChunk && a.ksize == 7;    // K-chunked mode: one accumulator set per filter row (7x7) ...
+            const bool blk_chunks = kChunk && !row_chunks;     // ... or per (channel block, term); (row chunks: tps == 1)
             uint32_t pi = 0, pph = 0, bi = 0, bph = 0, ai = 0, aph = 0;
             for (int t = work0; t < total_tiles; t += wstep) {
                 if (!kChunk) {
@@ -211,15 +235,18 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     for (int term = 0; term < nterms; ++term) {
                         // term 0 and 1 read the hi patch (against W_hi, W_lo), term 2 the residual patch (against W_hi)
                         if (term != 1) mbar_wait(&patch_full[pi], pph, 4);
+                        if (lane == 0 && t == work0) B2P_TL(2 + cb);        // 2, 3: patch of channel block 0 / 1 has landed
                         const bool release_patch = (term == nterms - 1) || (term == 1);
-                        uint32_t a_lo = patch_lo0 + pi * (kPatchBytes >> 4);     // window start of tap (0,0), sub-tile 0
+                        if (blk_chunks) {
+                            mbar_wait(&acc_empty[ai], aph ^ 1, 3);
+                            tc_fence_after();
+                            accumulate = 0;
+                        }
+                        uint32_t a_lo = patch_lo0 + pi * (kPatchBytes >> 4);     // window start of the next tap, sub-tile 0
                         int dx = 0;
-                        for (int tap = 0; tap < taps; ++tap) {
-                            // K-chunked mode: every filter row (7x7) / every (channel block, term) starts a fresh
-                            // accumulator set; the epilogue warps sum the chunks in fp32 registers
-                            const bool c_start = kChunk && (a.ksize == 7 ? dx == 0 : tap == 0);
-                            const bool c_end = kChunk && (a.ksize == 7 ? dx == a.ksize - 1 : tap == taps - 1);
-                            if (c_start) {
+                        for (int tap0 = 0; tap0 < taps; tap0 += tps) {          // one weight stage = tps consecutive taps
+                            const int cnt = taps - tap0 < tps ? taps - tap0 : tps;
+                            if (row_chunks && dx == 0) {
                                 mbar_wait(&acc_empty[ai], aph ^ 1, 3);
                                 tc_fence_after();
                                 accumulate = 0;
@@ -227,42 +254,72 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                             const uint32_t d_tmem = tmem_base + ai * 256;
                             mbar_wait(&b_full[bi], bph, 5);
                             tc_fence_after();
-                            const uint32_t b_lo = b_lo0 + bi * (kBStride >> 4);
+                            if (lane == 0 && t == work0 && cb == 0 && tap0 == 0) B2P_TL(4);   // first weight slice
+                            const bool c_end = row_chunks && dx == a.ksize - 1;
                             if (elect_one()) {
+                                uint32_t ta = a_lo, acc = accumulate;
+                                uint32_t b_lo = b_lo0 + bi * b_stage_step;
+                                int tdx = dx;
+                                for (int j = 0; j < cnt; ++j) {
 #pragma unroll
-                                for (int sub = 0; sub < 2; ++sub) {
+                                    for (int sub = 0; sub < 2; ++sub) {
+                                        if (sub >= nsub) break;
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        if (kPair)
-                                            umma_bf16_pair(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
-                                                           bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
-                                        else
-                                            umma_bf16(d_tmem + sub * 128, adesc_hi | (a_lo + sub * 64 + k * 2),
-                                                      bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? accumulate : 1u);
+                                        for (int k = 0; k < 4; ++k) {
+                                            if (kPair)
+                                                umma_bf16_pair(d_tmem + sub * 128, adesc_hi | (ta + sub * 64 + k * 2),
+                                                               bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? acc : 1u);
+                                            else
+                                                umma_bf16(d_tmem + sub * 128, adesc_hi | (ta + sub * 64 + k * 2),
+                                                          bdesc_hi | (b_lo + k * 2), idesc, k == 0 ? acc : 1u);
+                                        }
                                     }
+                                    acc = 1;
+                                    b_lo += b_tap_step;
+                                    ta += 8;                                      // next tap: one pixel (128 B) to the right
+                                    if (++tdx == a.ksize) { tdx = 0; ta += row_wrap; }
                                 }
-                                const bool tile_end = !kChunk && tap == taps - 1 && cb == a.cin_blocks - 1 && term == nterms - 1;
-                                if (kPair) {
-                                    umma_commit_pair(&b_empty[bi]);
-                                    if (tap == taps - 1 && release_patch) umma_commit_pair(&patch_empty[pi]);
-                                    if (tile_end || c_end) umma_commit_pair(&acc_full[ai]);
-                                } else {
-                                    umma_commit(&b_empty[bi]);
-                                    if (tap == taps - 1 && release_patch) umma_commit(&patch_empty[pi]);
-                                    if (tile_end || c_end) umma_commit(&acc_full[ai]);
+                                if (kPair) umma_commit_pair(&b_empty[bi]);
+                                else umma_commit(&b_empty[bi]);
+                                if (c_end) {
+                                    if (kPair) umma_commit_pair(&acc_full[ai]);
+                                    else umma_commit(&acc_full[ai]);
                                 }
                             }
                             __syncwarp();
                             accumulate = 1;
                             if (c_end) { if (++ai == 2) { ai = 0; aph ^= 1; } }
-                            if (++bi == kBStages) { bi = 0; bph ^= 1; }
-                            a_lo += 8;                                            // next tap: one pixel (128 B) to the right
-                            if (++dx == a.ksize) { dx = 0; a_lo += row_wrap; }
+                            if (++bi == nb) { bi = 0; bph ^= 1; }
+                            dx += cnt;                                            // every lane keeps the window position
+                            a_lo += cnt * 8;
+                            while (dx >= a.ksize) { dx -= a.ksize; a_lo += row_wrap; }
                         }
+                        if (blk_chunks || release_patch) {
+                            if (elect_one()) {      // (elect.sync names the same lane every time: the one that issued the MMAs)
+                                if (release_patch) {
+                                    if (kPair) umma_commit_pair(&patch_empty[pi]);
+                                    else umma_commit(&patch_empty[pi]);
+                                }
+                                if (blk_chunks) {
+                                    if (kPair) umma_commit_pair(&acc_full[ai]);
+                                    else umma_commit(&acc_full[ai]);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (blk_chunks) { if (++ai == 2) { ai = 0; aph ^= 1; } }
                         if (release_patch) { if (++pi == kNumPatchStages) { pi = 0; pph ^= 1; } }
                     }
                 }
-                if (!kChunk) { if (++ai == 2) { ai = 0; aph ^= 1; } }
+                if (!kChunk) {
+                    if (lane == 0 && t == work0) B2P_TL(5);                 // all MMAs of the first tile issued
+                    if (elect_one()) {
+                        if (kPair) umma_commit_pair(&acc_full[ai]);
+                        else umma_commit(&acc_full[ai]);
+                    }
+                    __syncwarp();
+                    if (++ai == 2) { ai = 0; aph ^= 1; }
+                }
             }
         }
     } else if (warp >= 2 && warp != 6) {
@@ -271,6 +328,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         // warps 7..10 cover 3,0,1,2 - two warps per quarter, which split the accumulator columns in 32-column chunks
         // (even chunks / odd chunks).  With one warp per quarter the layers with little MMA work per tile (Cin = 64, the
         // 1x1 layers, the pooled layers with their shuffles) were bound by this epilogue.
+        pdl_wait();               // (stores of this layer may overwrite what the previous layer still reads)
         const int q = warp & 3;   // TMEM lane quarter this warp may access
         const int half = warp >= 7 ? 1 : 0;
         const int h_in = q * 4 + (lane >> 3);
@@ -279,7 +337,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
         const int Wo = a.pool ? a.W >> 1 : a.W;
         uint32_t ai = 0, aph = 0;
         for (int t = work0; t < total_tiles; t += wstep) {
-            const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank);
+            const TileCoord tc = decode_tile<kPair>(t, a.n_tiles, a.groups, tiles_x, tiles_y, a.n_img, rank, tile_w);
             if (kChunk) {
                 // ---- K-chunked accumulation (n_tile <= 64: this warp owns ONE 32-column chunk of both sub-tiles) ----
                 float accr[2][32];
@@ -296,6 +354,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     if (mine) {
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
+                            if (sub >= nsub) break;
                             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ai * 256 + sub * 128 + c0;
                             uint32_t r[32];
                             if (full) tmem_ld32(taddr, r);
@@ -326,6 +385,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
                     const int f32_ch = a.f32_ch[tc.g];
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
+                        if (sub >= nsub) break;
                         const int y = tc.y0 + h_in;
                         const int x = tc.x0 + sub * 8 + w_in;
                         const bool valid = tc.valid && (y < a.H) && (x < a.W);
@@ -389,13 +449,14 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             }
             mbar_wait(&acc_full[ai], aph, 6);
             tc_fence_after();
+            if (warp == 2 && lane == 0 && t == work0) B2P_TL(6);                // first tile's accumulators complete
             const int ch_tile = tc.nt * a.n_tile;                    // first channel of this n-tile within the group
             const float* bias = a.bias + (tc.g * a.n_tiles + tc.nt) * a.n_tile;
             const int store_ch = a.store_ch[tc.g];
             float* of32 = a.out_f32[tc.g];
             const int f32_ch = a.f32_ch[tc.g];
 #pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
+            for (int sub = 0; sub < nsub; ++sub) {
                 const int y = tc.y0 + h_in;
                 const int x = tc.x0 + sub * 8 + w_in;
                 const bool valid = tc.valid && (y < a.H) && (x < a.W);
@@ -480,6 +541,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
             }
             tc_fence_before();
             __syncwarp();
+            if (warp == 2 && lane == 0 && t == work0) B2P_TL(7);                // first tile stored
             if (lane == 0) {
                 if (kPair) mbar_arrive_leader(&acc_empty[ai]);     // the leader's MMA warp waits for both CTAs' epilogues
                 else mbar_arrive(&acc_empty[ai]);
@@ -489,8 +551,10 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
     }
 
     tc_fence_before();
+    if (threadIdx.x == 0) B2P_TL(8);
     if (kPair) cluster_sync_all();      // both CTAs are done with each other's barriers / the pair's TMEM
     else __syncthreads();
+    if (threadIdx.x == 0) B2P_TL(9);
     if (warp == 1) {
         tc_fence_after();
         if (kPair) tmem_dealloc_pair(tmem_base, 512);
@@ -565,9 +629,17 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
         const int cin_pad = a.cin_blocks * 64;
         const int rows = a.groups * a.n_tiles * a.n_tile;
         const int taps = a.ksize * a.ksize;
+        // taps per weight stage: as many as leave kMinBStages stages in the ring (small n-tiles: 5 taps of 2 KB per stage for
+        // a CTA pair with N = 32; N = 128: one tap per stage as before).  The K-chunked 7x7 mode closes an accumulator set at
+        // every filter-row end, which a stage must not straddle.
+        const int tap_bytes = (a.pair ? a.n_tile / 2 : a.n_tile) * 128;
+        int tps = (kNumBStages * kBStageBytes) / (kMinBStages * tap_bytes);
+        if (tps < 1 || (a.chunk && a.ksize == 7)) tps = 1;
+        if (tps > taps) tps = taps;
+        a.tps = tps;
         cuuint64_t dims[3] = {(cuuint64_t)cin_pad, (cuuint64_t)rows, (cuuint64_t)(2 * taps)};
         cuuint64_t strides[2] = {(cuuint64_t)cin_pad * 2, (cuuint64_t)rows * cin_pad * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)(a.pair ? a.n_tile / 2 : a.n_tile), 1};
+        cuuint32_t box[3] = {64, (cuuint32_t)(a.pair ? a.n_tile / 2 : a.n_tile), (cuuint32_t)tps};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&a.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(w), dims, strides,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -581,11 +653,26 @@ cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cst
 }
 
 namespace {
-// (Programmatic dependent launch of consecutive layers was measured and rejected: the isolated network gains ~1 %, the
-// whole step loses ~2 % at batch 32 - 3214 vs 3297 frames/s - because the next layer's CTAs then win every freed SM
-// against the post-processing kernels of the previous batch; profiles/r02_ab_pdl.txt.)
+// Programmatic dependent launch (a.pdl): the next layer's CTAs may start - barrier init, TMEM allocation, descriptor
+// prefetch, weight loads - while this layer's last CTAs drain; they wait (griddepcontrol.wait) before touching activations.
+// Used by the SMALL-batch plans only, where the ~12 us fixed cost per launch is most of a layer.  At batch 32 it was measured
+// and rejected: the isolated network gains ~1 %, the whole step loses ~2 % (3214 vs 3297 frames/s) because the next layer's
+// CTAs then win every freed SM against the post-processing kernels of the previous batch.
 template <class Kernel>
 cudaError_t launch_plain(Kernel kernel, int grid, cudaStream_t stream, const ConvTcArgs& a) {
+    if (a.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kConvTcThreads);
+        cfg.dynamicSmemBytes = kConvTcSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, a);
+    }
     kernel<<<grid, kConvTcThreads, kConvTcSmemBytes, stream>>>(a);
     return cudaGetLastError();
 }
@@ -594,10 +681,11 @@ cudaError_t launch_plain(Kernel kernel, int grid, cudaStream_t stream, const Con
 cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream) {
     static DynSmemOptIn optin, optin_pair;   // per device: a second net on another GPU of the same process needs its own opt-in
     if (a.pool && ((a.H | a.W) & 1)) return cudaErrorInvalidValue;
-    const int tiles_x = (a.W + kTileW - 1) / kTileW;
+    const int tiles_x = (a.W + (a.narrow ? 8 : kTileW) - 1) / (a.narrow ? 8 : kTileW);
     const int tiles_y = (a.H + kTileH - 1) / kTileH;
     static DynSmemOptIn optin_chunk, optin_pair_chunk;
     if (a.chunk && a.n_tile > 64) return cudaErrorInvalidValue;      // one 32-column chunk per epilogue warp
+    if (a.tps < 1) return cudaErrorInvalidValue;                     // conv_tc_make_maps has not run
     if (a.pair) {
         const int pairs = ((a.n_img * tiles_y * tiles_x + 1) / 2) * a.groups * a.n_tiles;
         const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
@@ -622,5 +710,16 @@ cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream
     if (e != cudaSuccess) return e;
     return launch_plain(conv_tc_kernel, grid, stream, a);
 }
+
+#ifdef B2P_CONV_TIMELINE
+cudaError_t conv_tc_read_timeline(unsigned long long* out) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_conv_timeline, sizeof(g_conv_timeline));
+    if (e != cudaSuccess) return e;
+    void* p = nullptr;
+    e = cudaGetSymbolAddress(&p, g_conv_timeline);
+    if (e != cudaSuccess) return e;
+    return cudaMemset(p, 0, sizeof(g_conv_timeline));
+}
+#endif
 
 }  // namespace b2p

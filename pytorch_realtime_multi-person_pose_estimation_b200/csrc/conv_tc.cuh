@@ -16,15 +16,20 @@ constexpr int kMaxKs = 7;
 constexpr int kPatchBytes = kPatchPitch * (kTileH + kMaxKs - 1) * 128;  // 67,584 B per 64-channel block
 constexpr int kBStageBytes = 128 * 128;                                 // up to N=128 rows of 64 bf16
 #ifndef B2P_CONV_B_STAGES
-#define B2P_CONV_B_STAGES 2      // weight (B operand) ring: 2 x 16 KB stages, i.e. FOUR 8 KB half-slices in CTA-pair mode.  The
-                                 // shared memory a conv CTA leaves free decides which post-processing kernels of the previous
-                                 // batch can run NEXT to it: with 3 stages (185 KB) the small ones fit, taking everything (four
-                                 // patch stages, 230 KB) cost 9 % of the step (3 254 -> 2 947 frames/s); see DESIGN.md 2.4
+#define B2P_CONV_B_STAGES 3      // weight (B operand) ring: 48 KB, cut into stages of `tps` taps (conv_tc.cu): three stages of two 8 KB
+                                 // half-slices for a CTA pair with N = 128.  The shared memory a conv CTA leaves free decides which
+                                 // post-processing kernels of the previous batch can run NEXT to it: at 185 KB the small ones still
+                                 // fit; taking everything (four patch stages, 230 KB) cost 9 % of the step; see DESIGN.md 2.4
 #endif
 constexpr int kNumBStages = B2P_CONV_B_STAGES;
+#ifndef B2P_CONV_MIN_B_STAGES
+#define B2P_CONV_MIN_B_STAGES 3
+#endif
+constexpr int kMinBStages = B2P_CONV_MIN_B_STAGES;     // a stage holds as many taps as still leave this many stages in the ring
+constexpr int kMaxBStages = 16;       // the ring is cut into stages of the size the layer's n-tile needs (conv_tc.cu)
 constexpr int kNumPatchStages = 2;
 constexpr int kConvTcThreads = 352;   // warps: 0 patch TMA, 1 MMA, 2-5 and 7-10 epilogue (two per TMEM lane quarter), 6 weight TMA
-constexpr int kConvTcSmemBytes = kNumPatchStages * kPatchBytes + kNumBStages * kBStageBytes + 1024 /*align*/ + 256;
+constexpr int kConvTcSmemBytes = kNumPatchStages * kPatchBytes + kNumBStages * kBStageBytes + 1024 /*align*/ + 512;
 
 struct ConvTcArgs {
     // ---- geometry (stride 1, "same" padding, square kernel)
@@ -54,9 +59,15 @@ struct ConvTcArgs {
     int pair;
     // ---- K-chunked accumulation (n_tile <= 64): see conv_tc_chunk_kernel
     int chunk;
+    // ---- narrow tiles (small batches): the CTA tile is 8 x 16 pixels (one UMMA M=128 sub-tile) instead of 16 x 16
+    int narrow;
+    // ---- taps per weight stage (set by conv_tc_make_maps together with the weight map's box)
+    int tps;
+    // ---- programmatic dependent launch of this layer behind the previous one (small-batch plans)
+    int pdl;
     // ---- tensor maps
     CUtensorMap tm_in;        // 4D (C, W, H, N) bf16, box (64, 24, 16+ks-1, 1), SWIZZLE_128B
-    CUtensorMap tm_w;         // 3D (cin_pad, groups*n_tiles*n_tile, 2*taps) bf16 [hi taps | lo taps], box (64, n_tile, 1)
+    CUtensorMap tm_w;         // 3D (cin_pad, groups*n_tiles*n_tile, 2*taps) bf16 [hi taps | lo taps], box (64, n_tile, tps)
                               // (pair mode: box (64, n_tile / 2, 1) - each CTA of a pair loads its half of the N rows)
     CUtensorMap tm_in_lo;     // residual plane of the input (split mode)
 };
@@ -67,5 +78,11 @@ struct ConvTcArgs {
 cudaError_t conv_tc_make_maps(ConvTcArgs& a, const __nv_bfloat16* in, int in_cstride, const __nv_bfloat16* w,
                               const __nv_bfloat16* in_lo = nullptr);
 cudaError_t conv_tc_launch(const ConvTcArgs& a, int num_sms, cudaStream_t stream);
+
+#ifdef B2P_CONV_TIMELINE
+// Debug builds only (tools/conv_timeline.sh): clock64() stamps of the first 64 CTAs at the phase boundaries of conv_tc_body.
+constexpr int kTlSlots = 16;
+cudaError_t conv_tc_read_timeline(unsigned long long* out /*[64 * kTlSlots]*/);     // copies and clears
+#endif
 
 }  // namespace b2p

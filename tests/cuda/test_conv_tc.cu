@@ -32,7 +32,7 @@ struct Case {
 };
 
 // head: out_ch_off {0,40}, store {40,24}, f32 {38,19}; cout_g is the padded per-group Cout (n_tile).
-static int run_case(const Case& c, int use_bo, int num_sms, int pair, int chunk = 0) {
+static int run_case(const Case& c, int use_bo, int num_sms, int pair, int chunk = 0, int narrow = 0) {
     const int taps = c.ks * c.ks, pad = c.ks / 2;
     const int cin_blocks = c.cin_g / 64;
     const int in_c = (c.in_stride_g == 0) ? c.cin_g : c.cin_g * c.groups;
@@ -89,6 +89,7 @@ static int run_case(const Case& c, int use_bo, int num_sms, int pair, int chunk 
     a.use_base_offset = use_bo;
     a.pair = pair;
     a.chunk = chunk;
+    a.narrow = narrow;
     CK(conv_tc_make_maps(a, d_in, in_c, d_w));
     CK(conv_tc_launch(a, num_sms, 0));
     cudaError_t e = cudaDeviceSynchronize();
@@ -96,6 +97,22 @@ static int run_case(const Case& c, int use_bo, int num_sms, int pair, int chunk 
         printf("case %-28s bo=%d pair=%d : KERNEL FAILED: %s\n", c.name, use_bo, pair, cudaGetErrorString(e));
         return 100;
     }
+#ifdef B2P_CONV_TIMELINE
+    {
+        std::vector<unsigned long long> tl(64 * kTlSlots);
+        CK(conv_tc_read_timeline(tl.data()));
+        const char* names[10] = {"entry", "prologue done", "patch cb0", "patch cb1", "first weights", "MMAs issued", "acc complete",
+                                 "tile stored", "before final sync", "exit"};
+        for (int cta = 0; cta < 4; ++cta) {
+            printf("  timeline %s pair=%d chunk=%d narrow=%d CTA %d (clk since entry):", c.name, pair, chunk, narrow, cta);
+            for (int sl = 1; sl < 10; ++sl) {
+                const unsigned long long v = tl[cta * kTlSlots + sl], v0 = tl[cta * kTlSlots];
+                printf(" %s=%lld", names[sl], v ? (long long)(v - v0) : -1LL);
+            }
+            printf("\n");
+        }
+    }
+#endif
     std::vector<__nv_bfloat16> out_h(out_elems);
     CK(cudaMemcpy(out_h.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost));
     std::vector<float> f32_h[2];
@@ -162,8 +179,8 @@ static int run_case(const Case& c, int use_bo, int num_sms, int pair, int chunk 
                         }
                     }
                 }
-    printf("case %-28s bo=%d pair=%d chunk=%d : max|err| bf16 %.5f  f32 %.3e  (max|ref| %.3f)  bad=%ld  %s\n", c.name, use_bo,
-           pair, chunk, max_err, max_err32, max_ref, bad, bad == 0 ? "OK" : "MISMATCH");
+    printf("case %-28s bo=%d pair=%d chunk=%d narrow=%d : max|err| bf16 %.5f  f32 %.3e  (max|ref| %.3f)  bad=%ld  %s\n", c.name, use_bo,
+           pair, chunk, narrow, max_err, max_err32, max_ref, bad, bad == 0 ? "OK" : "MISMATCH");
     cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out);
     for (int g = 0; g < 2; ++g) if (d_f32[g]) cudaFree(d_f32[g]);
     return bad == 0 ? 0 : 1;
@@ -240,6 +257,8 @@ int main(int argc, char** argv) {
         {"3x3 64->128 odd tiles 3x40x16", 3, 40, 16, 3, 1, 64, 64, 128, 128, 1, 0, 0},     // 3 images x 3 x 1 = 9 pixel tiles (odd)
         {"7x7 2grp 128->128 1x16x16", 1, 16, 16, 7, 2, 128, 128, 128, 128, 1, 0, 0},        // ONE pixel tile: the odd CTA idles
         {"7x7 2grp 128->128 nt64 30x30", 1, 30, 30, 7, 2, 128, 128, 128, 64, 1, 0, 0},      // two 64-wide n-tiles per group
+        {"7x7 2grp 128->128 nt32 46x46", 1, 46, 46, 7, 2, 128, 128, 128, 32, 1, 0, 0},      // batch-1 plan: four 32-wide n-tiles
+        {"3x3 128->128 pool nt32 24x40", 1, 24, 40, 3, 1, 128, 128, 128, 32, 1, 1, 0},
         {"7x7 head 128->38|19 K=6272", 2, 46, 46, 7, 2, 128, 128, 48, 48, 0, 0, 1},          // fp32 outputs after a long K loop
     };
     // use_base_offset=0 is the product setting: the UMMA shared-memory descriptor swizzles on absolute smem address
@@ -251,12 +270,14 @@ int main(int argc, char** argv) {
         for (const Case& c : cases) {
             for (int pair = 0; pair <= ((c.n_tile % 32 == 0) ? 1 : 0); ++pair) {     // CTA-pair mode where it is eligible
                 for (int chunk = 0; chunk <= (c.n_tile <= 64 ? 1 : 0); ++chunk) {    // K-chunked accumulation (N <= 64)
-                    int r = run_case(c, bo, sms, pair, chunk);
-                    if (r >= 100) {   // sticky CUDA error: the context is gone
-                        printf("aborting after kernel failure\n");
-                        return 3;
+                    for (int narrow = 0; narrow <= 1; ++narrow) {                     // 8 x 16 pixel tiles (small batches)
+                        int r = run_case(c, bo, sms, pair, chunk, narrow);
+                        if (r >= 100) {   // sticky CUDA error: the context is gone
+                            printf("aborting after kernel failure\n");
+                            return 3;
+                        }
+                        if (bo == 0) fails += r;
                     }
-                    if (bo == 0) fails += r;
                 }
             }
         }

@@ -355,6 +355,39 @@ def test_uint8_input_path_fuses_rtpose_preprocess(native_net, he_sd):
     assert max(float((o.cpu() - s).abs().max()) for o, s in zip(outs, saved)) < FP32_TOL
 
 
+def test_graph_replay_equals_plain_launches(native_net):
+    """On a real stream the 52 launches of the forward pass are captured into a CUDA graph per (shape, mode, input
+    pointer) and replayed; on the legacy default stream they are launched one by one.  Same bits either way, also after
+    the input buffer's contents change, after a shape change in between, and for a second input pointer."""
+    nat = pkg_module("_native")
+    g = torch.Generator().manual_seed(17)
+    side = torch.cuda.Stream()
+
+    def run(xd, stream, mode):
+        n, _, H, W = xd.shape
+        outs = [torch.empty((n, 38 if i % 2 == 0 else 19, H // 8, W // 8), device="cuda") for i in range(12)]
+        native_net.forward_ptr(xd.data_ptr(), True, n, H, W, nat.MODES[mode], [o.data_ptr() for o in outs], True,
+                               stream.cuda_stream)
+        torch.cuda.synchronize()
+        return outs
+
+    for mode in ("bf16", "bf16x3"):
+        xa = (torch.rand((2, 3, 64, 72), generator=g) - 0.5).cuda()
+        xb = (torch.rand((2, 3, 64, 72), generator=g) - 0.5).cuda()
+        xc = (torch.rand((1, 3, 96, 64), generator=g) - 0.5).cuda()
+        torch.cuda.synchronize()
+        for rep in range(3):
+            if rep:
+                xa.copy_(torch.rand((2, 3, 64, 72), generator=g) - 0.5)      # same pointer, new frames
+                torch.cuda.synchronize()
+            for xd in (xa, xc, xb, xa):
+                want = run(xd, torch.cuda.default_stream(), mode)
+                got = run(xd, side, mode)
+                for a, b in zip(got, want):
+                    assert torch.equal(a, b)
+        assert float(want[-1].abs().max()) > 0.05
+
+
 def test_two_runs_in_flight_results_are_kept_apart(built):
     """Run i+1 may be submitted before run i is read: results land in parity slots of pinned host memory."""
     eng, nat = pkg_module("engine"), pkg_module("_native")

@@ -24,6 +24,11 @@ VARIANTS = {
     "bstages3": ["-DB2P_CONV_B_STAGES=3"],
     "gather256": ["-DB2P_GATHER_THREADS=256"],      # 256-thread gather blocks (16 K registers)
     "fit": ["-DB2P_GATHER_THREADS=256", "-DB2P_PEAK_THREADS=128"],
+    # conv weight ring (default: 48 KB, >= 3 stages -> CTA pair N=128: 2 taps per stage, 3 stages)
+    "ring32": ["-DB2P_CONV_B_STAGES=2"],                                  # N=128: 1 tap per stage, 4 stages (the round-2 mid state)
+    "ring48min2": ["-DB2P_CONV_MIN_B_STAGES=2"],                          # N=128: 3 taps per stage, 2 stages
+    "ring64": ["-DB2P_CONV_B_STAGES=4", "-DB2P_CONV_MIN_B_STAGES=4"],     # N=128: 2 taps per stage, 4 stages (201 KB)
+    "ring64min2": ["-DB2P_CONV_B_STAGES=4", "-DB2P_CONV_MIN_B_STAGES=2"], # N=128: 4 taps per stage, 2 stages
 }
 
 
