@@ -12,10 +12,11 @@
 //     shared memory.  Every one of the k*k filter taps then reads its shifted 8x16 window of that SAME patch
 //     directly through the UMMA shared-memory descriptor (start address = patch + (dy*24+dx)*128 B,
 //     8-row groups 24*128 B apart), so the activation tile is fetched from L2 once instead of k*k times.
-//   * Per tap, a TMA 3-D load brings the [n_tile x 64] weight slice (K-major, SWIZZLE_128B) into a 5-deep ring.
+//   * TMA 3-D loads bring the [n_tile x 64] weight slices (K-major, SWIZZLE_128B) of `tps` consecutive taps per stage into a
+//     48 KB ring (tps: as many taps as still leave three stages - the per-stage barrier / issue cost is ~360 clk).
 //   * One elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) into TMEM; two accumulator sets
 //     (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
-//   * Four epilogue warps read TMEM (tcgen05.ld 32x32b), add bias, ReLU, optionally 2x2 max-pool through warp
+//   * Eight epilogue warps (two per TMEM lane quarter) read TMEM (tcgen05.ld 32x32b), add bias, ReLU, optionally 2x2 max-pool through warp
 //     shuffles, convert to bf16 and store NHWC; the stage heads additionally emit the fp32 NCHW outputs.
 //   * Persistent grid (one CTA per SM), static round-robin tile schedule.
 //   * CTA-PAIR mode (a.pair, template kPair): the grid is launched as clusters of two CTAs on the two SMs of a TPC and the
@@ -94,6 +95,7 @@ __device__ __forceinline__ void conv_tc_body(const ConvTcArgs& a) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) B2P_TL(0);
 
     // narrow mode (small batches): the CTA tile is ONE 8 x 16 sub-tile - twice the CTAs, half the MMA work each; the patch
     // box keeps its 24-pixel pitch (the right part is loaded and not read)
