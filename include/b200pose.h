@@ -50,7 +50,12 @@ int b200pose_net_finalize(b200pose_net* net);
 /* forward: input fp32 NCHW [n,3,H,W] (H, W multiples of 8); outputs[12] fp32 NCHW in saved_for_loss order
  * [paf1, heat1, ..., paf6, heat6] (paf [n,38,H/8,W/8], heat [n,19,H/8,W/8]); entries may be NULL to skip the
  * copy-out.  *_on_device: 0 = host pointers (copies are issued on `cuda_stream` and synchronised before return),
- * 1 = device pointers (asynchronous on `cuda_stream`).  cuda_stream: a cudaStream_t cast to void* (NULL = default). */
+ * 1 = device pointers (asynchronous on `cuda_stream`).  cuda_stream: a cudaStream_t cast to void* (NULL = default).
+ * On a real stream (not the legacy default stream, not one that is being captured) the 52 launches of a SMALL-batch
+ * (launch-bound: up to 4 frames of 368x368) bf16 / bf16x3 forward pass are captured at the SECOND use of a (shape, mode, input pointer) into a CUDA graph and replayed afterwards
+ * (a caller that passes a fresh pointer every time never pays a capture); the input buffer's
+ * CONTENTS may change between calls, results are those of plain launches (tests/test_gpu.py:
+ * test_graph_replay_equals_plain_launches).  B200POSE_GRAPH=0 disables the capture. */
 int b200pose_net_forward(b200pose_net* net, const float* input, int input_on_device, int n, int H, int W, int mode,
                          float* const* outputs, int outputs_on_device, void* cuda_stream);
 /* Same, but the input is uint8 HWC BGR frames [n,H,W,3] (what cv2.imread / crop_with_factor produce) and
