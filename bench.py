@@ -9,6 +9,7 @@ configs[3]: batch 32 per B200, bf16, fused post-processing).  Weights: seeded He
 seeded uniform [-0.5, 0.5).  Prints ONE JSON line on rank 0.
 """
 import argparse
+import datetime
 import importlib
 import json
 import os
@@ -16,6 +17,7 @@ import statistics
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -45,41 +47,118 @@ def peaks(clocks):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """SM clock / power / throttle reasons DURING the timed region.  Two sources, because the timed region of the default
+    run is only ~0.2 s: an NVML thread (nvidia_ml_py) that samples every 10 ms between mark_start() and stop(), and an
+    `nvidia-smi -lms 100` process started ahead of the warm-up whose time-stamped rows are filtered to the same window (the
+    fallback when NVML is not importable; if no row falls inside the window the nearest one is used and named)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
+        self.t0 = self.t1 = None
+        self.nv_rows, self.nv_stop, self.nv_thread, self.nv_handle, self.nv = [], threading.Event(), None, None, None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        # nvidia-smi / NVML count physical GPUs: the CUDA index only matches when CUDA_VISIBLE_DEVICES does not remap it
+        remapped = bool(os.environ.get("CUDA_VISIBLE_DEVICES"))
+        sel = str(uuid) if (uuid and remapped) else str(gpu_index)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+            self.p = subprocess.Popen(["nvidia-smi", "-i", sel, "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.nv_handle = None
+            if uuid and remapped:
+                for u in (str(uuid), str(uuid).encode()):
+                    try:
+                        self.nv_handle = pynvml.nvmlDeviceGetHandleByUUID(u)
+                        break
+                    except Exception:
+                        pass
+            if self.nv_handle is None:
+                self.nv_handle = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+            self.nv_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.nv_handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = self.nv_handle = None
+
+    def _nv_loop(self):
+        nv, h = self.nv, self.nv_handle
+        while not self.nv_stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.nv_rows.append((sm, pw, rs))
+            except Exception:
+                break
+            self.nv_stop.wait(0.01)
+
+    def mark_start(self):
+        self.t0 = datetime.datetime.now()
+        if self.nv_handle is not None:
+            self.nv_thread = threading.Thread(target=self._nv_loop, daemon=True)
+            self.nv_thread.start()
 
     def stop(self):
+        self.t1 = datetime.datetime.now()
+        self.nv_stop.set()
+        if self.nv_thread is not None:
+            self.nv_thread.join(timeout=2)
+        smi = self._stop_smi()
+        if self.nv_rows:
+            sm = [r[0] for r in self.nv_rows]
+            reasons = sorted({name for r in self.nv_rows for bit, name in self.BITS if r[2] & bit})
+            return {"sm_mhz": statistics.median(sm), "sm_max_mhz": self.nv_max, "power_w_max": round(max(r[1] for r in self.nv_rows), 2),
+                    "samples": len(self.nv_rows), "reasons": reasons, "source": "nvml, every 10 ms inside the timed region"}
+        return smi
+
+    def _stop_smi(self):
         if self.p is None:
             return None
+        time.sleep(0.12)                      # let the row that covers the end of the window be written
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [l.split(",") for l in open(self.f.name).read().strip().splitlines() if l.count(",") >= 8]
+        rows = []
+        for l in open(self.f.name).read().strip().splitlines():
+            r = [c.strip() for c in l.split(",")]
+            if len(r) < 9:
+                continue
+            try:
+                rows.append((datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f"), r))
+            except Exception:
+                continue
         os.unlink(self.f.name)
         if not rows:
             return None
-        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        t0 = self.t0 or rows[0][0]
+        inside = [r for ts, r in rows if t0 <= ts <= self.t1]
+        source = "nvidia-smi -lms 100, rows inside the timed region"
+        if not inside:
+            ts, r = min(rows, key=lambda x: abs((x[0] - t0).total_seconds()))
+            inside = [r]
+            source = "nvidia-smi: nearest row, %+.0f ms from the start of the timed region" % ((ts - t0).total_seconds() * 1e3)
+        sm = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in rows:
+        for r in inside:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower() == "active":
+                if v.lower() == "active":
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][2]),
-                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(inside[0][2]),
+                "power_w_max": max(float(r[3]) for r in inside), "samples": len(inside), "reasons": sorted(reasons),
+                "source": source}
 
 
 def synthetic_weights():
@@ -160,6 +239,18 @@ def run_ours(args):
         d2h_bytes.append(4 * BATCH * (1 + 1 + 18) + nh * 73 * 4)
         return nh
 
+    sampler = None
+    if rank == 0:       # (started ahead of the warm-up: nvidia-smi needs ~0.3 s to come up; only rows inside the timed region count)
+        try:
+            gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+            if not gpu_uuid.startswith("GPU-"):
+                gpu_uuid = "GPU-" + gpu_uuid
+        except Exception:
+            gpu_uuid = None
+        try:
+            sampler = ClockSampler(local, gpu_uuid)
+        except Exception:
+            sampler = None
     for i in range(args.warmup):
         step_device(i)
     torch.cuda.synchronize()
@@ -167,7 +258,8 @@ def run_ours(args):
 
     # ---- device-resident timing (value)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     l0 = nat.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
