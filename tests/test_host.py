@@ -585,3 +585,44 @@ def test_pose_stream_pipelines_two_batches(built):
         list(streaming.PoseStream(FakeModel(), [frames[0], np.zeros((50, 64, 3), np.uint8)], batch=2, draw=False))
     with pytest.raises(nat.B200PoseError):
         streaming.PoseStream(object(), frames)
+
+
+def test_bench_clock_sampler_keeps_only_rows_inside_the_timed_region():
+    """bench.py's clock record must describe the TIMED region: rows of the nvidia-smi poller (started ahead of the
+    warm-up) are filtered by their time stamps; with no row inside the window the nearest one is used and named; the
+    roofline denominator follows the record (burst only at full clock without a power cap)."""
+    import datetime
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Done:     # stands for the poller process
+        def terminate(self): pass
+        def wait(self, timeout=None): pass
+        def kill(self): pass
+
+    def sampler_with(rows, t0):
+        s = bench.ClockSampler(0, None)
+        if s.p is not None:
+            s.p.kill()
+        s.p, s.nv_handle, s.nv_rows = Done(), None, []
+        with open(s.f.name, "w") as f:
+            for dt_ms, mhz, cap in rows:
+                ts = (t0 + datetime.timedelta(milliseconds=dt_ms)).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+                f.write("%s, %d, 1965, 250.5, 0x0, Not Active, Not Active, Not Active, %s\n"
+                        % (ts, mhz, "Active" if cap else "Not Active"))
+        s.t0 = t0
+        return s
+
+    now = datetime.datetime.now()
+    s = sampler_with([(-300, 1200, True), (-100, 1500, True), (50, 1965, False), (150, 1965, False), (9000, 900, True)], now)
+    time.sleep(0.25)
+    rec = s.stop()
+    assert rec["samples"] == 2 and rec["sm_mhz"] == 1965.0 and rec["reasons"] == [] and "inside" in rec["source"]
+    assert "burst" in bench.peaks(rec)[2]
+    s = sampler_with([(-400, 1500, True)], datetime.datetime.now())
+    rec = s.stop()
+    assert rec["samples"] == 1 and rec["reasons"] == ["sw_power_cap"] and "nearest" in rec["source"]
+    assert "sustained" in bench.peaks(rec)[2] and "sustained" in bench.peaks(None)[2]
